@@ -1,0 +1,181 @@
+/*
+ * sbd.h -- C-ABI of the B200-native sea-breeze trigger ("sbd" = sea-breeze diagnostic).
+ *
+ * Drop-in boundary for the hot path of antarcticrainforest/seabreeze_param.  Every entry point
+ * replaces one reference routine; citations are file:line under the reference tree:
+ *   G = generic/sea_breeze_diag.f90             (module sea_breeze_diag_mod, Fortran host models)
+ *   H = generic/halo_exchange_mod.f90           (swap_bounds)
+ *   P = python_wrapper/seabreezediag/seabreeze_diag_python.f90   (f2py module `seabreeze`)
+ *   S = python_wrapper/seabreezediag/sobel.f90                  (f2py module `seabreeze`)
+ *   U = UM/vn10.7/sea_breeze_diag.F90           (UM hook; same C-ABI, `error` = return status)
+ *
+ * Conventions
+ *  - plain C, no CUDA / torch types.  All arrays are binary32, column-major (Fortran order),
+ *    longitude (x) fastest: a(j,i[,k]) -> a[(k*ny + i)*nx + j] with 0-based i,j,k.
+ *  - every pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer on the current
+ *    CUDA device; the library detects which (cudaPointerGetAttributes).  Host data is staged
+ *    through library-owned device buffers and the call blocks until outputs are back (reference
+ *    semantics).  With device pointers the work is enqueued on the plan's stream and the call
+ *    returns immediately (use sbd_plan_sync / the stream to wait).
+ *  - return value: 0 = ok, 1 = bad dimensions (the UM variant's `error = 1`, U:198-201),
+ *    2 = invalid argument, 3 = CUDA failure (sbd_last_error() has the text).
+ *  - there is NO CPU fallback: without a usable CUDA device every entry point returns 3.
+ *  - transcendental functions are the pinned algorithms of sbd_math.h (see there).
+ *
+ * "halo'd" arrays are (nx+2h) x (ny+2h) with the nx x ny interior at offset (h,h)
+ * (UM convention tdims_s / tdims_l, U:78-117).
+ */
+#ifndef SBD_H
+#define SBD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBD_OK 0
+#define SBD_EDIMS 1
+#define SBD_EINVAL 2
+#define SBD_ECUDA 3
+
+#define SBD_VARIANT_GENERIC 0 /* G / U: halo'd neighbour fields, 3-D p, windspeed updated every step */
+#define SBD_VARIANT_PYTHON 1  /* P / S: index-mapped boundaries, 1-D p, 6-hourly windspeed update    */
+
+/* Tunables.  Generic/UM: compile-time parameters G:127-138 / U:158-169.  Python: runtime optional
+ * arguments P:137-141 (already converted to SI here: Pa, s). */
+typedef struct sbd_params {
+  float target_plev;    /* Pa   (70000)     */
+  float thresh_wind;    /* m/s  (11)        */
+  float thresh_winddir; /* deg  (90)        */
+  float thresh_windch;  /* m/s  (5)         */
+  float thresh_thc;     /* K    (0.75)      */
+  float target_time;    /* s    (21600)     */
+  float maxdist;        /* km   (180)       */
+  float gmma;           /* K/m  (-0.0060956)*/
+  float rad2deg;        /*      (57.2957)   */
+  float missing;        /* sb_con far from the coast: 0.0 (G:176) or 2.0E20 (P:173) */
+  int level_scan;       /* 0 = minloc (G:223), 1 = early-exit scan (U:265-274) */
+} sbd_params;
+
+void sbd_default_params(sbd_params* prm, int variant);
+const char* sbd_last_error(void);
+/* Number of usable CUDA devices (0 => every compute entry point fails with SBD_ECUDA). */
+int sbd_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generic (Fortran host model) entry points: what an ISO_C_BINDING shim named
+ * sea_breeze_diag_mod forwards to (fortran/sea_breeze_diag_mod.f90).
+ * ------------------------------------------------------------------------------------------- */
+
+/* get_edges(mask, icefrac, landfrac, halo_size)  G:273-373.
+ * mask: halo'd, out.  icefrac, landfrac: nx x ny.  swap != 0 fills the halos at the two
+ * swap_bounds call sites (G:342, G:371) with sbd_swap_bounds_f32; swap == 0 leaves the halos as
+ * the caller supplied them (the literal no-op stub H:12-17).
+ * m1 (optional, nx*ny bytes): binarised land/ice mask (G:325-337). */
+int sbd_get_edges_f32(float* mask, const float* icefrac, const float* landfrac, int nx, int ny, int h,
+                      int swap, uint8_t* m1);
+
+/* get_dist(coast, landfrac, lon, lat, maxdist, cdist, halo_size)  G:375-455.
+ * coast: halo'd output of get_edges; landfrac, cdist: nx x ny; lon(nx), lat(ny) in degrees.
+ * Search radius = h cells (G:422,425). */
+int sbd_get_dist_f32(const float* coast, const float* landfrac, const float* lon, const float* lat,
+                     float maxdist, float* cdist, int nx, int ny, int h);
+
+/* sigmoid(ary, sm)  G:457-481.  stats (optional, 4 floats): mean, 2/sigma, r, var. */
+int sbd_sigmoid_f32(const float* ary, float* sm, int nx, int ny, float* stats);
+
+/* seabreeze_diag(timestep, timestep_number, p,u,v, theta, mask, z, sigma, windspeed, winddir, thc,
+ * sb_con)  G:55-271 (U:55-326 with level_scan=1; its `error` is the return value).
+ * p,u,v: nx x ny x nz.  theta, mask (signed coast distance), z, sigma: halo'd.
+ * windspeed, winddir, thc, sb_con: nx x ny, inout.  flags (optional, nx*ny bytes):
+ * bit0 = coastal zone |mask|<=maxdist (G:174), bit1 = trigger (G:249-252). */
+int sbd_seabreeze_diag_f32(float timestep, int timestep_number, const float* p, const float* u,
+                           const float* v, const float* theta, const float* mask, const float* z,
+                           const float* sigma, float* windspeed, float* winddir, float* thc,
+                           float* sb_con, int nx, int ny, int nz, int h, const sbd_params* prm,
+                           uint8_t* flags);
+
+/* swap_bounds(field, halo_size)  H:12-17 (stub) / U:408-410.  Single-domain halo fill:
+ * east-west periodic, north-south edge-replicated.  The multi-GPU halo swap (NCCL send/recv between
+ * row blocks) lives in seabreeze_param_b200/halo.py and uses sbd_swap_bounds_ew_f32 for the local
+ * periodic part. */
+int sbd_swap_bounds_f32(float* field, int nx, int ny, int h);
+int sbd_swap_bounds_ew_f32(float* field, int nx, int ny, int h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Python (f2py module `seabreeze`) entry points: same positional meaning as the f2py signatures.
+ * ------------------------------------------------------------------------------------------- */
+
+/* coast = get_edges(lsm, ci, [nlons, nlats])  S:19-89 */
+int sbd_py_get_edges_f32(const float* lsm, const float* ci, int nlons, int nlats, float* coast);
+
+/* cdist = get_dist(coast, mask, lon, lat, [nlons, nlats, maxdist=180])  S:91-193.
+ * k_out (optional): the search radius derived at S:129-137. */
+int sbd_py_get_dist_f32(const float* coast, const float* mask, const float* lon, const float* lat,
+                        int nlons, int nlats, float maxdist, float* cdist, int* k_out);
+
+/* sm = sigmoid(ary, [nlons, nlats])  P:287-311 */
+int sbd_py_sigmoid_f32(const float* ary, int nlons, int nlats, float* sm);
+
+/* output = diag(timestep_number, p, z, std, theta, v, u, cdist, windspeed, winddir, thc,
+ *               [target_plev=700, thresh_wind=11, thresh_winddir=90, thresh_windch=5,
+ *                thresh_thc=0.75, target_time=6, maxdist=180, timestep=24, nps, nlons, nlats])
+ * P:49-285.  Units as in the f2py signature (hPa, h, min).  output: (nlons,nlats,4) =
+ * sb_con, t0, windspeed, winddir.  flags optional as above. */
+int sbd_py_diag_f32(int timestep_number, const float* p, const float* z, const float* std,
+                    const float* theta, const float* v, const float* u, const float* cdist,
+                    const float* windspeed, const float* winddir, const float* thc, float target_plev,
+                    float thresh_wind, float thresh_winddir, float thresh_windch, float thresh_thc,
+                    float target_time, float maxdist, float timestep, int nps, int nlons, int nlats,
+                    float* output, uint8_t* flags);
+
+/* nt = get_threads()  S:195-206: here the number of CUDA devices. */
+int sbd_get_threads(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Plan API: device-resident, static fields processed once (what a host model that calls
+ * seabreeze_diag every timestep with unchanged mask/z/sigma wants).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sbd_plan sbd_plan;
+
+/* variant: SBD_VARIANT_*.  nz: levels of p,u,v (python: nps).  h: halo (generic) -- ignored for
+ * python.  prm may be NULL (defaults of the variant). */
+int sbd_plan_create(sbd_plan** plan, int variant, int nx, int ny, int nz, int h, const sbd_params* prm);
+void sbd_plan_destroy(sbd_plan* plan);
+/* Use an external CUDA stream (cudaStream_t cast to void*); NULL restores the plan's own. */
+int sbd_plan_set_stream(sbd_plan* plan, void* stream);
+void* sbd_plan_get_stream(sbd_plan* plan);
+int sbd_plan_sync(sbd_plan* plan);
+
+/* Static fields: mask = signed coast distance, z, sigma (generic: halo'd; python: nlons x nlats).
+ * Computes the sigmoid statistics (sequential-order exact), the sea-level correction plane
+ * gmma*z*sigmoid(sigma), the land/sea sign plane and every cell's final search radius nn.
+ * stats_in (optional, 3 floats mean, 2/sigma, r): use externally chained global statistics
+ * (multi-GPU row blocks) instead of computing them from this block. */
+int sbd_plan_set_static(sbd_plan* plan, const float* mask, const float* z, const float* sigma,
+                        const float* stats_in);
+/* Largest search radius found by set_static and the sigmoid statistics (mean, 2/sigma, r, var). */
+int sbd_plan_info(sbd_plan* plan, int* nn_max, int* n_coastal, float* stats4);
+
+/* One timestep, generic variant (G:170-269 after G:166-167). */
+int sbd_plan_step(sbd_plan* plan, float timestep, int timestep_number, const float* p, const float* u,
+                  const float* v, const float* theta, float* windspeed, float* winddir, float* thc,
+                  float* sb_con, uint8_t* flags);
+/* One time record, python variant (P:160-284).  timestep in minutes as in P. */
+int sbd_plan_step_py(sbd_plan* plan, int timestep_number, float timestep_min, const float* p,
+                     const float* u, const float* v, const float* theta, const float* windspeed,
+                     const float* winddir, float* output, uint8_t* flags);
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+unsigned long long sbd_launch_count(void);
+
+/* Sequential-order statistics with carry, for chaining across row blocks in rank order:
+ * pass 0: carry[0] = running sum (in/out), carry[2], carry[3] = running max, min (in/out; first=1
+ *         initialises them from the data);
+ * pass 1: carry[1] = running variance numerator (in/out) given mean in carry[4]. */
+int sbd_stats_chain_f32(const float* ary, int nx, int ny, int ld, int pass, int first, float* carry5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBD_H */

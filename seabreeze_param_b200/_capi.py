@@ -1,0 +1,117 @@
+"""ctypes binding of include/sbd.h.  Fails loudly when the CUDA library is missing: there is no
+CPU fallback anywhere in this package."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+SBD_VARIANT_GENERIC = 0
+SBD_VARIANT_PYTHON = 1
+
+# every symbol declared in include/sbd.h (tests check that the library exports all of them)
+SYMBOLS = [
+    "sbd_default_params", "sbd_last_error", "sbd_device_count",
+    "sbd_get_edges_f32", "sbd_get_dist_f32", "sbd_sigmoid_f32", "sbd_seabreeze_diag_f32",
+    "sbd_swap_bounds_f32", "sbd_swap_bounds_ew_f32",
+    "sbd_py_get_edges_f32", "sbd_py_get_dist_f32", "sbd_py_sigmoid_f32", "sbd_py_diag_f32",
+    "sbd_get_threads",
+    "sbd_plan_create", "sbd_plan_destroy", "sbd_plan_set_stream", "sbd_plan_get_stream",
+    "sbd_plan_sync", "sbd_plan_set_static", "sbd_plan_info", "sbd_plan_step", "sbd_plan_step_py",
+    "sbd_launch_count", "sbd_stats_chain_f32",
+]
+
+
+class SbdParams(C.Structure):
+    _fields_ = [
+        ("target_plev", C.c_float), ("thresh_wind", C.c_float), ("thresh_winddir", C.c_float),
+        ("thresh_windch", C.c_float), ("thresh_thc", C.c_float), ("target_time", C.c_float),
+        ("maxdist", C.c_float), ("gmma", C.c_float), ("rad2deg", C.c_float), ("missing", C.c_float),
+        ("level_scan", C.c_int),
+    ]
+
+
+class SbdError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.OUT
+
+
+def load():
+    """Load (building first if the sources are newer) the C-ABI shared library."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.OUT
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this machine and no prebuilt .so
+            if not os.path.exists(path):
+                raise SbdError(
+                    "libsbd_b200.so is missing and cannot be built (%s). The sea-breeze trigger has "
+                    "no CPU fallback: build it with `python -m seabreeze_param_b200.build`." % e)
+    lib = C.CDLL(path)
+    vp, fp, ip, i, f = C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_float
+    lib.sbd_default_params.argtypes = [C.POINTER(SbdParams), i]
+    lib.sbd_default_params.restype = None
+    lib.sbd_last_error.restype = C.c_char_p
+    lib.sbd_device_count.restype = i
+    lib.sbd_get_threads.restype = i
+    lib.sbd_launch_count.restype = C.c_ulonglong
+    lib.sbd_get_edges_f32.argtypes = [fp, fp, fp, i, i, i, i, vp]
+    lib.sbd_get_dist_f32.argtypes = [fp, fp, fp, fp, f, fp, i, i, i]
+    lib.sbd_sigmoid_f32.argtypes = [fp, fp, i, i, fp]
+    lib.sbd_seabreeze_diag_f32.argtypes = [f, i, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i, i, i, i,
+                                           C.POINTER(SbdParams), vp]
+    lib.sbd_swap_bounds_f32.argtypes = [fp, i, i, i]
+    lib.sbd_swap_bounds_ew_f32.argtypes = [fp, i, i, i]
+    lib.sbd_py_get_edges_f32.argtypes = [fp, fp, i, i, fp]
+    lib.sbd_py_get_dist_f32.argtypes = [fp, fp, fp, fp, i, i, f, fp, ip]
+    lib.sbd_py_sigmoid_f32.argtypes = [fp, i, i, fp]
+    lib.sbd_py_diag_f32.argtypes = [i, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, f, f, f, f, f, f, f, f, i, i, i,
+                                    fp, vp]
+    lib.sbd_plan_create.argtypes = [C.POINTER(vp), i, i, i, i, i, C.POINTER(SbdParams)]
+    lib.sbd_plan_destroy.argtypes = [vp]
+    lib.sbd_plan_destroy.restype = None
+    lib.sbd_plan_set_stream.argtypes = [vp, vp]
+    lib.sbd_plan_get_stream.argtypes = [vp]
+    lib.sbd_plan_get_stream.restype = vp
+    lib.sbd_plan_sync.argtypes = [vp]
+    lib.sbd_plan_set_static.argtypes = [vp, fp, fp, fp, fp]
+    lib.sbd_plan_info.argtypes = [vp, ip, ip, fp]
+    lib.sbd_plan_step.argtypes = [vp, f, i, fp, fp, fp, fp, fp, fp, fp, fp, vp]
+    lib.sbd_plan_step_py.argtypes = [vp, i, f, fp, fp, fp, fp, fp, fp, fp, vp]
+    lib.sbd_stats_chain_f32.argtypes = [fp, i, i, i, i, i, fp]
+    _LIB = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().sbd_last_error().decode(errors="replace")
+        raise SbdError("%s failed with status %d: %s" % (what or "sbd call", rc, msg))
+
+
+def ptr(a):
+    """Raw address of a numpy array, torch tensor (host or CUDA), int address, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError("cannot take the address of %r" % type(a))
+
+
+def default_params(variant):
+    p = SbdParams()
+    load().sbd_default_params(C.byref(p), variant)
+    return p

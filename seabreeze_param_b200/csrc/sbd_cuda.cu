@@ -1,0 +1,1303 @@
+// sbd_cuda.cu -- sm_100a kernels + C-ABI (include/sbd.h) of the sea-breeze trigger hot path.
+//
+// From-scratch B200 implementation of get_edges / get_dist / sigmoid / seabreeze_diag
+// (reference: generic/sea_breeze_diag.f90 = G, python_wrapper/seabreezediag/{seabreeze_diag_python,
+// sobel}.f90 = P, S).  Not a port: the Fortran's scatter, growing-window re-summation and
+// per-call statistics are replaced by gather / final-window / plan-cached forms that are
+// bit-identical to the reference's sequential evaluation order.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA contraction: the
+// reference arithmetic has separate multiplies and adds; include/sbd_math.h relies on it too).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "sbd.h"
+#include "sbd_math.h"
+
+// ------------------------------------------------------------------------------------------------
+// error handling / bookkeeping
+// ------------------------------------------------------------------------------------------------
+namespace sbdk {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      snprintf(g_err, sizeof g_err, "%s:%d %s -> %s", __FILE__, __LINE__, #call,                  \
+               cudaGetErrorString(e_));                                                           \
+      return SBD_ECUDA;                                                                           \
+    }                                                                                             \
+  } while (0)
+
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+int fail(int code, const char* msg)
+{
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  return code;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+bool is_device_ptr(const void* p)
+{
+  if (!p) return false;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// A device view of a caller array: either the caller's device pointer or a staged copy.
+struct Staged {
+  float* d = nullptr;
+  bool owned = false;
+};
+
+constexpr float kR = 6370.9989f;      // S:113
+constexpr float kPi = 3.1415926f;     // S:114
+constexpr float kD2R = kPi / 180.0f;  // S:116
+
+// ------------------------------------------------------------------------------------------------
+// geometry: how window / stencil offsets map to memory (SURVEY A.4, A.5 "boundary")
+// ------------------------------------------------------------------------------------------------
+struct Geo {
+  int nx, ny;  // interior size
+  int h;       // halo (generic) / 0 (python)
+  int ldx;     // row pitch of the 2-D neighbour-read planes
+  int ldy;     // rows of those planes
+};
+
+// GENERIC: raw halo'd index (G:200-201).  PYTHON: ki = clamp(ii), kj = max(1, modulo(jj, nlons))
+// (P:201-202, S:67-68) in 0-based form: the last column is never a neighbour, both jj=0 and
+// jj=nlons (1-based) land on column 1.
+template <int VARIANT>
+__device__ __forceinline__ int nbr_index(const Geo& g, int gx, int gy)
+{
+  if (VARIANT == SBD_VARIANT_GENERIC) {
+    int x = min(max(gx + g.h, 0), g.ldx - 1);
+    int y = min(max(gy + g.h, 0), g.ldy - 1);
+    return y * g.ldx + x;
+  } else {
+    int m = (gx + 1) % g.nx;
+    if (m < 0) m += g.nx;
+    const int col = (m == 0) ? 0 : m - 1;
+    const int row = min(max(gy, 0), g.ny - 1);
+    return row * g.nx + col;
+  }
+}
+template <int VARIANT>
+__device__ __forceinline__ int own_index(const Geo& g, int gx, int gy)
+{
+  if (VARIANT == SBD_VARIANT_GENERIC) return (gy + g.h) * g.ldx + (gx + g.h);
+  return gy * g.nx + gx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 edges
+// ------------------------------------------------------------------------------------------------
+// generic binarise (G:325-337) into the halo'd mask interior
+__global__ void k_binarise_generic(float* __restrict__ mask, const float* __restrict__ ice,
+                                   const float* __restrict__ land, int nx, int ny, int h,
+                                   uint8_t* __restrict__ m1)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= nx) return;
+  const size_t c = (size_t)y * nx + x;
+  const float ic = ice[c], ld = land[c];
+  float m;
+  if (ic <= 0.2f) m = (ld >= 0.5f) ? 1.0f : 0.0f;
+  else m = (ld + ic >= 0.5f) ? 1.0f : 0.0f;
+  mask[(size_t)(y + h) * (nx + 2 * h) + (x + h)] = m;
+  if (m1) m1[c] = (uint8_t)m;
+}
+
+// Sobel on the halo'd binary mask (G:348-366): coast = (px != 0 || py != 0).  Values are small
+// integers, exactly representable, so integer arithmetic is bit-equivalent to the fp32 original.
+__global__ void k_sobel_generic(const float* __restrict__ mask, float* __restrict__ coast, int nx,
+                                int ny, int h)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= nx) return;
+  const int ldx = nx + 2 * h;
+  const float* r0 = mask + (size_t)(y + h - 1) * ldx + (x + h);
+  const float* r1 = r0 + ldx;
+  const float* r2 = r1 + ldx;
+  // px = sum_i (1,2,1)_i (m(x+1,y+i) - m(x-1,y+i));  py = sum_j (1,2,1)_j (m(x+j,y+1) - m(x+j,y-1))
+  const float px = (r0[1] - r0[-1]) + 2.0f * (r1[1] - r1[-1]) + (r2[1] - r2[-1]);
+  const float py = (r2[-1] - r0[-1]) + 2.0f * (r2[0] - r0[0]) + (r2[1] - r0[1]);
+  coast[(size_t)y * nx + x] = (px != 0.0f || py != 0.0f) ? 1.0f : 0.0f;
+}
+
+__global__ void k_copy_interior(float* __restrict__ dst_h, const float* __restrict__ src, int nx, int ny,
+                                int h)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= nx) return;
+  dst_h[(size_t)(y + h) * (nx + 2 * h) + (x + h)] = src[(size_t)y * nx + x];
+}
+__global__ void k_extract_interior(float* __restrict__ dst, const float* __restrict__ src_h, int nx,
+                                   int ny, int h)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= nx) return;
+  dst[(size_t)y * nx + x] = src_h[(size_t)(y + h) * (nx + 2 * h) + (x + h)];
+}
+
+// halo fill: east-west periodic on interior rows ...
+__global__ void k_halo_ew(float* __restrict__ f, int nx, int ny, int h)
+{
+  const int t = threadIdx.x;  // 0..2h-1
+  const int y = blockIdx.x + h;
+  if (t >= 2 * h) return;
+  float* row = f + (size_t)y * (nx + 2 * h);
+  if (t < h) {
+    int s = (t - h) % nx; if (s < 0) s += nx;
+    row[t] = row[h + s];
+  } else {
+    const int tt = t - h;
+    row[nx + h + tt] = row[h + (tt % nx)];
+  }
+}
+// ... then north-south edge replication of whole rows (including the E-W halos just filled)
+__global__ void k_halo_ns(float* __restrict__ f, int nx, int ny, int h)
+{
+  const int ldx = nx + 2 * h;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;  // 0..2h-1
+  if (x >= ldx) return;
+  if (t < h) f[(size_t)t * ldx + x] = f[(size_t)h * ldx + x];
+  else f[(size_t)(ny + h + (t - h)) * ldx + x] = f[(size_t)(ny + h - 1) * ldx + x];
+}
+
+// python get_edges (S:58-88): mask = (lsm+ci) > 0.4 evaluated at neighbour-read time.
+__global__ void k_edges_py(const float* __restrict__ lsm, const float* __restrict__ ci,
+                           float* __restrict__ coast, int nx, int ny)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= nx) return;
+  Geo g{nx, ny, 0, nx, ny};
+  int m[3][3];
+#pragma unroll
+  for (int i = -1; i <= 1; ++i)
+#pragma unroll
+    for (int j = -1; j <= 1; ++j) {
+      const int s = nbr_index<SBD_VARIANT_PYTHON>(g, x + j, y + i);
+      m[i + 1][j + 1] = ((lsm[s] + ci[s]) > 0.4f) ? 1 : 0;
+    }
+  const int px = (m[0][2] - m[0][0]) + 2 * (m[1][2] - m[1][0]) + (m[2][2] - m[2][0]);
+  const int py = (m[2][0] - m[0][0]) + 2 * (m[2][1] - m[0][1]) + (m[2][2] - m[0][2]);
+  coast[(size_t)y * nx + x] = (px != 0 || py != 0) ? 1.0f : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 dist: gather form of the scatter at S:152-192
+// ------------------------------------------------------------------------------------------------
+// tables: phi (lat in rad), cphi = cos(phi), lcorr = d2r*(lon [-360 if > 180])
+__global__ void k_dist_tab1(const float* __restrict__ lon, const float* __restrict__ lat, int nx, int ny,
+                            float* __restrict__ phi, float* __restrict__ cphi, float* __restrict__ lcorr)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ny) {
+    const float p = kD2R * lat[t];
+    phi[t] = p;
+    cphi[t] = sbd_cosf(p);
+  }
+  if (t < nx) {
+    const float l = lon[t];
+    lcorr[t] = (l > 180.0f) ? kD2R * (l - 360.0f) : kD2R * l;
+  }
+}
+// S1[yy][di+k] = sin((phi(i)-phi(yy))/2)^2, i = yy+di;  S2[xx][dj+k] = sin((l(j)-l(xx))/2)^2, j = wrap(xx+dj)
+__global__ void k_dist_tab2(const float* __restrict__ phi, const float* __restrict__ lcorr, int nx, int ny,
+                            int k, float* __restrict__ S1, float* __restrict__ S2)
+{
+  const int w = 2 * k + 1;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n1 = (long long)ny * w, n2 = (long long)nx * w;
+  if (t < n1) {
+    const int yy = (int)(t / w), di = (int)(t % w) - k;
+    const int i = yy + di;
+    float v = 0.0f;
+    if (i >= 0 && i < ny) {
+      const float dphi = phi[i] - phi[yy];
+      const float s = sbd_sinf(dphi / 2.0f);
+      v = s * s;
+    }
+    S1[t] = v;
+  } else if (t < n1 + n2) {
+    const long long q = t - n1;
+    const int xx = (int)(q / w), dj = (int)(q % w) - k;
+    int j = (xx + dj) % nx; if (j < 0) j += nx;
+    const float dlam = lcorr[j] - lcorr[xx];
+    const float s = sbd_sinf(dlam / 2.0f);
+    S2[q] = s * s;
+  }
+}
+// coast bit rows
+__global__ void k_coast_bits(const float* __restrict__ coast, int nx, int ny, int ld, int off,
+                             uint32_t* __restrict__ bits, int wpr)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const bool on = (x < nx) && (coast[(size_t)y * ld + off + x] > 0.0f);
+  const uint32_t b = __ballot_sync(0xffffffffu, on);
+  if ((threadIdx.x & 31) == 0 && (x >> 5) < wpr) bits[(size_t)y * wpr + (x >> 5)] = b;
+}
+
+__device__ __forceinline__ float hav_c(float a)
+{
+  const float R2 = kR * 2.0f;
+  return R2 * sbd_atan2f(sqrtf(a), sqrtf(1.0f - a)) + 0.5f;  // S:177
+}
+
+__global__ void __launch_bounds__(128)
+k_dist_gather(const uint32_t* __restrict__ bits, int wpr, const float* __restrict__ landmask,
+              const float* __restrict__ cphi, const float* __restrict__ S1, const float* __restrict__ S2,
+              int nx, int ny, int k, float maxdist, float* __restrict__ cdist)
+{
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yy = blockIdx.y;
+  if (xx >= nx) return;
+  const int w = 2 * k + 1;
+  const float cX = cphi[yy];
+  const float* s2row = S2 + (size_t)xx * w + k;  // index by dj
+  const float* s1row = S1 + (size_t)yy * w + k;  // index by di
+  const float INF = __int_as_float(0x7f800000);
+  float amin_e = INF, amin_l = INF;
+  const int L = min(w, nx);
+  int js = (xx - k) % nx; if (js < 0) js += nx;
+  const int i0 = max(0, yy - k), i1 = min(ny - 1, yy + k);
+  for (int i = i0; i <= i1; ++i) {
+    const float s1 = s1row[i - yy];
+    const float cP = cphi[i];
+    const uint32_t* brow = bits + (size_t)i * wpr;
+    // up to two linear column ranges [ja, jb]
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+      int ja, jb;
+      if (part == 0) { ja = js; jb = min(js + L, nx) - 1; }
+      else { ja = 0; jb = js + L - nx - 1; }
+      if (jb < ja) continue;
+      for (int wd = ja >> 5; wd <= (jb >> 5); ++wd) {
+        uint32_t m = brow[wd];
+        if (!m) continue;
+        const int base = wd << 5;
+        if (base < ja) m &= 0xffffffffu << (ja - base);
+        if (base + 31 > jb) m &= 0xffffffffu >> (base + 31 - jb);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int j = base + b;
+          int dj = (j - xx + k) % nx; if (dj < 0) dj += nx;
+          dj -= k;
+          const float s2 = s2row[dj];
+          const float a = s1 + (cP * (cX * s2));  // S:176
+          const bool earlier = (i < yy) || (i == yy && j <= xx);
+          if (earlier) amin_e = fminf(amin_e, a);
+          else amin_l = fminf(amin_l, a);
+        }
+      }
+    }
+  }
+  float e = 12000.0f;
+  bool far = true;
+  if (amin_e < INF) {
+    e = hav_c(amin_e);
+    far = !(e < 12000.0f);
+    if (far) e = 12000.0f;
+  }
+  if (fabsf(e) > 2.0f * maxdist) { e = 12000.0f; far = true; }  // S:188
+  float l = INF;
+  if (amin_l < INF) l = hav_c(amin_l);
+  const bool land = landmask[(size_t)yy * nx + xx] > 0.0f;  // S:179
+  float out;
+  if (l < e) out = land ? l : -l;
+  else out = far ? 12000.0f : (land ? e : -e);
+  cdist[(size_t)yy * nx + xx] = out;
+}
+
+// search radius k (S:129-137), evaluated by one thread so that the pinned math runs on the device
+__global__ void k_dist_radius(const float* __restrict__ lon, const float* __restrict__ lat, int nx, int ny,
+                              float maxdist, int* __restrict__ kout)
+{
+  if (threadIdx.x || blockIdx.x) return;
+  int tlat = 0;
+  float best = fabsf(70.0f - lat[0]);
+  for (int i = 1; i < ny; ++i) {
+    const float d = fabsf(70.0f - lat[i]);
+    if (d < best) { best = d; tlat = i; }
+  }
+  if (tlat + 1 >= ny || nx < 2) { *kout = -1; return; }
+  const float p0 = kD2R * lat[tlat], p1 = kD2R * lat[tlat + 1];
+  const float dphi = p1 - p0;
+  const float dlam = kD2R * lon[1] - kD2R * lon[0];
+  const float s1 = sbd_sinf(dphi / 2.0f), s2 = sbd_sinf(dlam / 2.0f);
+  const float a = s1 * s1 + (sbd_cosf(p1) * (sbd_cosf(p0) * (s2 * s2)));
+  const float dx = kR * 2.0f * sbd_atan2f(sqrtf(a), sqrtf(1.0f - a));
+  const float q = maxdist / dx;
+  *kout = (q < 1.0e9f) ? (int)q : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 stats: the reference's sequential fp32 chain (G:466-478), reproduced in order.
+// One warp: coalesced 32-element loads, then the dependent add chain over shuffled values.
+// carry[0]=sum carry[1]=var carry[2]=max carry[3]=min carry[4]=mean (see sbd_stats_chain_f32)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_stats_seq(const float* __restrict__ ary, int nx, int ny, int ld, int pass, int first,
+                            float* __restrict__ carry)
+{
+  const int lane = threadIdx.x;
+  const long long n = (long long)nx * ny;
+  float acc = (pass == 0) ? carry[0] : carry[1];
+  const float mean = carry[4];
+  float mx = first ? -__int_as_float(0x7f800000) : carry[2];
+  float mn = first ? __int_as_float(0x7f800000) : carry[3];
+  for (long long base = 0; base < n; base += 32) {
+    const long long t = base + lane;
+    float v = 0.0f;
+    if (t < n) {
+      const int y = (int)(t / nx), x = (int)(t % nx);
+      v = ary[(size_t)y * ld + x];
+      if (pass == 0) { mx = fmaxf(mx, v); mn = fminf(mn, v); }
+      else { const float d = v - mean; v = d * d; }
+    }
+    const int cnt = (int)min(32LL, n - base);
+    if (cnt == 32) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc = acc + __shfl_sync(0xffffffffu, v, k);
+    } else {
+      for (int k = 0; k < cnt; ++k) acc = acc + __shfl_sync(0xffffffffu, v, k);
+    }
+  }
+  if (pass == 0) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+  }
+  if (lane == 0) {
+    if (pass == 0) { carry[0] = acc; carry[2] = mx; carry[3] = mn; }
+    else carry[1] = acc;
+  }
+}
+// stats[0]=mean (from sum), then after pass 1: stats[1]=2/sqrt(var/n), stats[2]=(max-min)/4, stats[3]=var
+__global__ void k_stats_finish(float* __restrict__ carry, float fn, int stage, float* __restrict__ stats)
+{
+  if (threadIdx.x || blockIdx.x) return;
+  if (stage == 0) {
+    const float mean = carry[0] / fn;  // G:466
+    carry[4] = mean;
+    carry[1] = 0.0f;
+  } else {
+    stats[0] = carry[4];
+    stats[1] = 2.0f / sqrtf(carry[1] / fn);     // G:478
+    stats[2] = (carry[2] - carry[3]) / 4.0f;    // G:479
+    stats[3] = carry[1];
+  }
+}
+// sm = 1/(1+exp(-std*(ary-r)))  G:480
+__global__ void k_sigmoid_apply(const float* __restrict__ ary, float* __restrict__ sm, long long n,
+                                const float* __restrict__ stats)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float nstd = -stats[1], r = stats[2];
+  sm[t] = 1.0f / (1.0f + sbd_expf(nstd * (ary[t] - r)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// static planes of a plan
+//   gzsm = (gmma*z)*sigmoid(sigma)            (so that t0 = theta - gzsm, G:167)
+//   code = bit15: land (mask >= 0, G:200) | bits0..14: final search radius nn (0 = not in the
+//          coastal zone / not processed)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_static_gzsm(const float* __restrict__ z, const float* __restrict__ sigma,
+                              float* __restrict__ gzsm, long long n, const float* __restrict__ stats,
+                              float gmma)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float nstd = -stats[1], r = stats[2];
+  const float sm = 1.0f / (1.0f + sbd_expf(nstd * (sigma[t] - r)));
+  gzsm[t] = (gmma * z[t]) * sm;
+}
+
+template <int VARIANT>
+__global__ void k_static_code(const float* __restrict__ mask, uint16_t* __restrict__ code, Geo g,
+                              float maxdist, int nncap, int rows_processed, int* __restrict__ nn_max,
+                              int* __restrict__ n_coastal)
+{
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;  // plane coordinates
+  const int py = blockIdx.y;
+  if (px >= g.ldx) return;
+  const int s = py * g.ldx + px;
+  const float m = mask[s];
+  uint32_t c = (m >= 0.0f) ? 0x8000u : 0u;
+  const int gx = px - g.h, gy = py - g.h;
+  const bool interior = gx >= 0 && gx < g.nx && gy >= 0 && gy < rows_processed;
+  if (interior && !(fabsf(m) > maxdist)) {
+    bool hl = false, hs = false;
+    int nn = 1;
+    // ring 0 + ring 1 first, then one ring per step (windows are nested, G:191-214)
+    for (;;) {
+      const int lo = (nn == 1) ? 0 : nn;
+      for (int r = lo; r <= nn && !(hl && hs); ++r) {
+        if (r == 0) {
+          if (mask[nbr_index<VARIANT>(g, gx, gy)] >= 0.0f) hl = true; else hs = true;
+          continue;
+        }
+        for (int d = -r; d <= r; ++d) {
+          // top & bottom rows of the ring
+          if (mask[nbr_index<VARIANT>(g, gx + d, gy - r)] >= 0.0f) hl = true; else hs = true;
+          if (mask[nbr_index<VARIANT>(g, gx + d, gy + r)] >= 0.0f) hl = true; else hs = true;
+        }
+        for (int d = -r + 1; d <= r - 1; ++d) {
+          if (mask[nbr_index<VARIANT>(g, gx - r, gy + d)] >= 0.0f) hl = true; else hs = true;
+          if (mask[nbr_index<VARIANT>(g, gx + r, gy + d)] >= 0.0f) hl = true; else hs = true;
+        }
+      }
+      if ((hl && hs) || nn >= nncap) break;
+      nn = nn + 1;
+    }
+    c |= (uint32_t)min(nn, 0x7fff);
+    atomicMax(nn_max, nn);
+    atomicAdd(n_coastal, 1);
+  }
+  code[s] = (uint16_t)c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 trigger: fused per-step kernel.
+//   tile (TX x TY interior cells) + halo R of t0 = theta - gzsm and the land bit -> shared memory;
+//   per coastal cell: sequential raster sum over its final (2nn+1)^2 window (bit-identical to the
+//   reference's last pass of G:191-214), level search over p, wind, thresholds, state update.
+// ------------------------------------------------------------------------------------------------
+struct TrigArgs {
+  Geo g;
+  int nz;
+  int R;               // tile halo held in shared memory
+  int rows_processed;  // ny (generic) / ny-1 (python, P:165)
+  int first_step;      // timestep_number < 2
+  int six_hourly;      // modulo(step*dt, target_time) < 1e-4
+  sbd_params prm;
+  const float* theta;    // neighbour-read plane
+  const float* gzsm;     // neighbour-read plane (static)
+  const uint16_t* code;  // neighbour-read plane (static)
+  const float* p;        // generic: nx*ny*nz ; python: nz
+  const float* u;
+  const float* v;
+  // generic state/outputs (nx x ny)
+  float* ws; float* wd; float* thc; float* sb;
+  // python: inputs ws_in, wd_in; output (nx,ny,4)
+  const float* ws_in; const float* wd_in; float* out;
+  uint8_t* flags;
+};
+
+template <int VARIANT>
+__device__ __forceinline__ void window_sums_global(const TrigArgs& a, int gx, int gy, int nn, float& T_l,
+                                                   float& T_s, uint32_t& c_l, uint32_t& c_s)
+{
+  for (int ii = gy - nn; ii <= gy + nn; ++ii)
+    for (int jj = gx - nn; jj <= gx + nn; ++jj) {
+      const int s = nbr_index<VARIANT>(a.g, jj, ii);
+      const float t = a.theta[s] - a.gzsm[s];
+      if (a.code[s] & 0x8000u) { T_l = T_l + t; ++c_l; }
+      else { T_s = T_s + t; ++c_s; }
+    }
+}
+
+template <int VARIANT, int TX, int TY, int NT>
+__global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
+{
+  constexpr int CPT = TX * TY / NT;  // cells per thread
+  static_assert(TX % 32 == 0 && NT % TX == 0 && (TX * TY) % NT == 0, "tile shape");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int R = a.R;
+  const int W = TX + 2 * R, Hh = TY + 2 * R;
+  float* s_t0 = reinterpret_cast<float*>(smem_raw);
+  uint8_t* s_land = reinterpret_cast<uint8_t*>(s_t0 + W * Hh);
+  __shared__ int s_lev;
+
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int tid = threadIdx.x;
+
+  // ---- python: one pressure level for the whole grid (P:228), first minimum of |p - target| ----
+  if (VARIANT == SBD_VARIANT_PYTHON && tid == 0) {
+    int lev = 0;
+    float best = fabsf(a.p[0] - a.prm.target_plev);
+    for (int k = 1; k < a.nz; ++k) {
+      const float d = fabsf(a.p[k] - a.prm.target_plev);
+      if (d < best) { best = d; lev = k; }
+    }
+    s_lev = lev;
+  }
+
+  // ---- phase 1: stage t0 and the land bit for the tile + halo ----
+  for (int idx = tid; idx < W * Hh; idx += NT) {
+    const int ly = idx / W, lx = idx - ly * W;
+    const int s = nbr_index<VARIANT>(a.g, x0 - R + lx, y0 - R + ly);
+    s_t0[idx] = a.theta[s] - a.gzsm[s];  // G:167
+    s_land[idx] = (uint8_t)(a.code[s] >> 15);
+  }
+  __syncthreads();
+
+  const int cx = tid % TX;
+  const int cy0 = (tid / TX) * CPT;
+  const size_t n2 = (size_t)a.g.nx * a.g.ny;
+
+  float n_thc[CPT];
+  bool active[CPT];   // coastal zone & processed
+  bool inside[CPT];
+#pragma unroll
+  for (int q = 0; q < CPT; ++q) {
+    const int gx = x0 + cx, gy = y0 + cy0 + q;
+    inside[q] = gx < a.g.nx && gy < a.g.ny;
+    active[q] = false;
+    n_thc[q] = 0.0f;
+    if (!inside[q]) continue;
+    const uint32_t cd = a.code[own_index<VARIANT>(a.g, gx, gy)];
+    const int nn = (int)(cd & 0x7fffu);
+    if (nn == 0) continue;
+    active[q] = true;
+    float T_l = 0.0f, T_s = 0.0f;
+    uint32_t c_l = 0, c_s = 0;
+    if (nn <= R) {
+      const int lcx = R + cx, lcy = R + cy0 + q;
+      for (int ii = lcy - nn; ii <= lcy + nn; ++ii) {
+        const float* tr = s_t0 + ii * W;
+        const uint8_t* lr = s_land + ii * W;
+        for (int jj = lcx - nn; jj <= lcx + nn; ++jj) {
+          const float t = tr[jj];
+          if (lr[jj]) { T_l = T_l + t; ++c_l; }   // G:200-202
+          else { T_s = T_s + t; ++c_s; }          // G:204-205
+        }
+      }
+    } else {
+      window_sums_global<VARIANT>(a, gx, gy, nn, T_l, T_s, c_l, c_s);
+    }
+    // n_l, n_s are fp32 counters in the reference: n = n + 1 saturates at 2^24
+    const float n_l = (float)min(c_l, 16777216u), n_s = (float)min(c_s, 16777216u);
+    const float mul = (cd & 0x8000u) ? 1.0f : -1.0f;        // G:182-186
+    n_thc[q] = mul * ((T_l / n_l) - (T_s / n_s));            // G:216
+  }
+
+  // ---- phase 2: pressure level, wind, thresholds, state ----
+  int lev[CPT];
+  if (VARIANT == SBD_VARIANT_GENERIC) {
+    float best[CPT];
+    const float tp = a.prm.target_plev;
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) { lev[q] = 0; best[q] = __int_as_float(0x7f800000); }
+    if (a.prm.level_scan == 0) {
+      // minloc(abs(p(j,i,:) - target_plev)), first minimum (G:223)
+#pragma unroll 4
+      for (int k = 0; k < a.nz; ++k) {
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+          if (active[q]) {
+            const size_t c = (size_t)(y0 + cy0 + q) * a.g.nx + (x0 + cx);
+            const float d = fabsf(__ldg(a.p + (size_t)k * n2 + c) - tp);
+            if (k == 0 || d < best[q]) { best[q] = d; lev[q] = k; }
+          }
+        }
+      }
+    } else {
+      // early-exit scan with <= (U:265-274)
+#pragma unroll
+      for (int q = 0; q < CPT; ++q) {
+        if (!active[q]) continue;
+        const size_t c = (size_t)(y0 + cy0 + q) * a.g.nx + (x0 + cx);
+        float diff = 1000000.0f;
+        for (int k = 0; k < a.nz; ++k) {
+          const float d = fabsf(__ldg(a.p + (size_t)k * n2 + c) - tp);
+          if (d <= diff) { lev[q] = k; diff = d; } else break;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) lev[q] = s_lev;
+  }
+
+#pragma unroll
+  for (int q = 0; q < CPT; ++q) {
+    if (!inside[q]) continue;
+    const int gx = x0 + cx, gy = y0 + cy0 + q;
+    const size_t c = (size_t)gy * a.g.nx + gx;
+    uint8_t fl = 0;
+    if (VARIANT == SBD_VARIANT_GENERIC) {
+      if (!active[q]) {
+        a.sb[c] = a.prm.missing;  // G:176
+        if (a.flags) a.flags[c] = 0;
+        continue;
+      }
+    }
+    float ws = 0.0f, wd = 0.0f, sb = a.prm.missing;
+    if (VARIANT == SBD_VARIANT_PYTHON) { ws = a.ws_in[c]; wd = a.wd_in[c]; }
+    float n_ws = 0.0f, n_wd = 0.0f;
+    if (active[q]) {
+      fl = 1;
+      const float uu = __ldg(a.u + (size_t)lev[q] * n2 + c), vv = __ldg(a.v + (size_t)lev[q] * n2 + c);
+      n_ws = sqrtf(uu * uu + vv * vv);                                   // G:225
+      n_wd = sbd_atan2f(-1.0f * uu, -1.0f * vv) * a.prm.rad2deg;         // G:227
+      if (VARIANT == SBD_VARIANT_GENERIC) {
+        if (a.first_step) { ws = n_ws; wd = n_wd; }                      // G:235-239
+        else { ws = a.ws[c]; wd = a.wd[c]; }
+      } else {
+        if (a.first_step) { ws = n_ws; wd = n_wd; }                      // P:236-240
+      }
+      const float thc_abs = fabsf(n_thc[q]);                             // G:242
+      const float mws = (ws + n_ws) / 2.0f;                              // G:243
+      const float dws = fabsf(ws - n_ws);                                // G:244
+      const float dwd = fabsf(sbd_modulo((wd - n_wd) + 180.0f, 360.0f) - 180.0f);  // G:246-247
+      if (dwd < a.prm.thresh_winddir && dws < a.prm.thresh_windch && mws < a.prm.thresh_wind &&
+          thc_abs > a.prm.thresh_thc) {                                  // G:249-252
+        const float scale_wind = (a.prm.thresh_wind - mws) / fmaxf(1.0f, mws);  // G:254
+        const float scale_thc = (thc_abs - a.prm.thresh_thc) / n_thc[q];        // G:255
+        sb = scale_thc * scale_wind;                                             // G:256
+        fl |= 2;
+      } else {
+        sb = 0.0f;                                                       // G:258
+      }
+    }
+    if (VARIANT == SBD_VARIANT_GENERIC) {
+      a.sb[c] = sb;
+      a.ws[c] = n_ws;                                                    // G:261
+      a.thc[c] = n_thc[q];                                               // G:262
+      if (a.six_hourly || a.first_step) a.wd[c] = n_wd;                  // G:237, G:264-266
+    } else {
+      if (active[q] && a.six_hourly) { ws = n_ws; wd = n_wd; }           // P:271-274
+      const int so = own_index<VARIANT>(a.g, gx, gy);
+      a.out[c] = sb;                                                     // P:277
+      a.out[n2 + c] = a.theta[so] - a.gzsm[so];                          // P:278
+      a.out[2 * n2 + c] = ws;                                            // P:279
+      a.out[3 * n2 + c] = wd;                                            // P:280
+    }
+    if (a.flags) a.flags[c] = fl;
+  }
+}
+
+}  // namespace sbdk
+using namespace sbdk;
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct sbd_plan {
+  int variant, nx, ny, nz, h;
+  Geo g;
+  sbd_params prm;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  // static planes
+  float* d_gzsm = nullptr;
+  uint16_t* d_code = nullptr;
+  float* d_stats = nullptr;   // 4 floats
+  float* d_carry = nullptr;   // 5 floats
+  int* d_cnt = nullptr;       // nn_max, n_coastal
+  int nn_max = 0, n_coastal = 0;
+  float stats[4] = {0, 0, 0, 0};
+  bool have_static = false;
+  int R = 0;
+  // staging (host-pointer calls); grown on demand
+  std::vector<std::pair<void*, size_t>> stage;
+  size_t stage_used = 0;
+};
+
+namespace {
+
+size_t plane_elems(const sbd_plan* p) { return (size_t)p->g.ldx * p->g.ldy; }
+
+// grab a staging buffer slot (slots are reused in call order across steps)
+int stage_get(sbd_plan* p, size_t bytes, void** out)
+{
+  if (p->stage_used < p->stage.size()) {
+    auto& s = p->stage[p->stage_used];
+    if (s.second < bytes) {
+      CK(cudaFree(s.first));
+      s.first = nullptr; s.second = 0;
+      CK(cudaMalloc(&s.first, bytes));
+      s.second = bytes;
+    }
+    *out = s.first;
+  } else {
+    void* d = nullptr;
+    CK(cudaMalloc(&d, bytes));
+    p->stage.emplace_back(d, bytes);
+    *out = d;
+  }
+  p->stage_used++;
+  return SBD_OK;
+}
+
+// device view of an input array
+int in_view(sbd_plan* p, const float* src, size_t n, const float** out)
+{
+  if (is_device_ptr(src)) { *out = src; return SBD_OK; }
+  void* d;
+  int rc = stage_get(p, n * sizeof(float), &d);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  *out = (const float*)d;
+  return SBD_OK;
+}
+// device view of an inout / out array; copy_in: upload the current host contents
+struct OutView { void* host = nullptr; void* dev = nullptr; size_t bytes = 0; };
+int out_view(sbd_plan* p, void* dst, size_t bytes, bool copy_in, void** dev, std::vector<OutView>& pend)
+{
+  if (!dst) { *dev = nullptr; return SBD_OK; }
+  if (is_device_ptr(dst)) { *dev = dst; return SBD_OK; }
+  void* d;
+  int rc = stage_get(p, bytes, &d);
+  if (rc) return rc;
+  if (copy_in) CK(cudaMemcpyAsync(d, dst, bytes, cudaMemcpyHostToDevice, p->stream));
+  pend.push_back({dst, d, bytes});
+  *dev = d;
+  return SBD_OK;
+}
+int flush_out(sbd_plan* p, std::vector<OutView>& pend, bool any_host)
+{
+  for (auto& o : pend) CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, p->stream));
+  if (any_host || !pend.empty()) CK(cudaStreamSynchronize(p->stream));
+  return SBD_OK;
+}
+
+int run_stats(cudaStream_t st, const float* d_ary, int nx, int ny, int ld, float* d_carry, float* d_stats)
+{
+  const float fn = (float)(nx * ny);  // real(nlons*nlats)
+  k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, 0, 1, d_carry); LAUNCHED();
+  k_stats_finish<<<1, 1, 0, st>>>(d_carry, fn, 0, d_stats); LAUNCHED();
+  k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, 1, 0, d_carry); LAUNCHED();
+  k_stats_finish<<<1, 1, 0, st>>>(d_carry, fn, 1, d_stats); LAUNCHED();
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+
+int swap_bounds_dev(cudaStream_t st, float* d_f, int nx, int ny, int h, bool ns)
+{
+  if (h <= 0) return SBD_OK;
+  k_halo_ew<<<ny, 2 * h, 0, st>>>(d_f, nx, ny, h); LAUNCHED();
+  if (ns) {
+    dim3 g(cdiv(nx + 2 * h, 128), 2 * h);
+    k_halo_ns<<<g, 128, 0, st>>>(d_f, nx, ny, h); LAUNCHED();
+  }
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+
+// get_dist core on device arrays (coast may be strided/halo'd)
+int dist_dev(cudaStream_t st, const float* d_coast, int coast_ld, int coast_off, const float* d_land,
+             const float* d_lon, const float* d_lat, int nx, int ny, int k, float maxdist, float* d_cdist)
+{
+  const int w = 2 * k + 1;
+  const int wpr = cdiv(nx, 32);
+  float *phi, *cphi, *lcorr, *S1, *S2;
+  uint32_t* bits;
+  CK(cudaMallocAsync((void**)&phi, sizeof(float) * ny, st));
+  CK(cudaMallocAsync((void**)&cphi, sizeof(float) * ny, st));
+  CK(cudaMallocAsync((void**)&lcorr, sizeof(float) * nx, st));
+  CK(cudaMallocAsync((void**)&S1, sizeof(float) * (size_t)ny * w, st));
+  CK(cudaMallocAsync((void**)&S2, sizeof(float) * (size_t)nx * w, st));
+  CK(cudaMallocAsync((void**)&bits, sizeof(uint32_t) * (size_t)ny * wpr, st));
+  k_dist_tab1<<<cdiv(max(nx, ny), 128), 128, 0, st>>>(d_lon, d_lat, nx, ny, phi, cphi, lcorr); LAUNCHED();
+  const long long nt = (long long)(nx + ny) * w;
+  k_dist_tab2<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(phi, lcorr, nx, ny, k, S1, S2); LAUNCHED();
+  {
+    dim3 g(cdiv(nx, 128), ny);
+    k_coast_bits<<<g, 128, 0, st>>>(d_coast, nx, ny, coast_ld, coast_off, bits, wpr); LAUNCHED();
+    k_dist_gather<<<g, 128, 0, st>>>(bits, wpr, d_land, cphi, S1, S2, nx, ny, k, maxdist, d_cdist); LAUNCHED();
+  }
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(phi, st)); CK(cudaFreeAsync(cphi, st)); CK(cudaFreeAsync(lcorr, st));
+  CK(cudaFreeAsync(S1, st)); CK(cudaFreeAsync(S2, st)); CK(cudaFreeAsync(bits, st));
+  return SBD_OK;
+}
+
+template <int VARIANT>
+int launch_trigger(sbd_plan* p, TrigArgs& a)
+{
+  constexpr int TX = 64, TY = 16, NT = 256;
+  const int R = a.R;
+  const size_t smem = (size_t)(TX + 2 * R) * (TY + 2 * R) * 5;
+  auto kern = k_trigger<VARIANT, TX, TY, NT>;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+  kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+
+int ensure_device()
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    return fail(SBD_ECUDA, "no usable CUDA device: the sea-breeze trigger has no CPU fallback");
+  }
+  return SBD_OK;
+}
+
+// temporary plan-less staging helper for the one-shot 2-D entry points
+struct Tmp {
+  cudaStream_t st = nullptr;
+  std::vector<void*> bufs;
+  std::vector<OutView> pend;
+  bool any_host = false;
+  ~Tmp() { for (void* b : bufs) cudaFree(b); }
+  int in(const float* src, size_t n, const float** out)
+  {
+    if (is_device_ptr(src)) { *out = src; return SBD_OK; }
+    any_host = true;
+    void* d; CK(cudaMalloc(&d, n * sizeof(float))); bufs.push_back(d);
+    CK(cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    *out = (const float*)d; return SBD_OK;
+  }
+  int out(void* dst, size_t bytes, bool copy_in, void** dev)
+  {
+    if (!dst) { *dev = nullptr; return SBD_OK; }
+    if (is_device_ptr(dst)) { *dev = dst; return SBD_OK; }
+    any_host = true;
+    void* d; CK(cudaMalloc(&d, bytes)); bufs.push_back(d);
+    if (copy_in) CK(cudaMemcpyAsync(d, dst, bytes, cudaMemcpyHostToDevice, st));
+    pend.push_back({dst, d, bytes}); *dev = d; return SBD_OK;
+  }
+  int scratch(size_t bytes, void** dev)
+  {
+    void* d; CK(cudaMalloc(&d, bytes)); bufs.push_back(d); *dev = d; return SBD_OK;
+  }
+  int finish()
+  {
+    for (auto& o : pend) CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SBD_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* sbd_last_error(void) { return g_err; }
+unsigned long long sbd_launch_count(void) { return g_launches.load(); }
+
+int sbd_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int sbd_get_threads(void) { return sbd_device_count(); }
+
+void sbd_default_params(sbd_params* q, int variant)
+{
+  q->target_plev = 100.0f * 700.0f;  // G:129
+  q->thresh_wind = 11.0f;
+  q->thresh_winddir = 90.0f;
+  q->thresh_windch = 5.0f;
+  q->thresh_thc = 0.75f;
+  q->target_time = 6.0f * 3600.0f;   // G:134
+  q->maxdist = 180.0f;
+  q->gmma = -0.0060956f;
+  q->rad2deg = 57.2957f;
+  q->missing = (variant == SBD_VARIANT_PYTHON) ? 2.0E20f : 0.0f;
+  q->level_scan = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, const sbd_params* prm)
+{
+  if (!out) return fail(SBD_EINVAL, "plan pointer is NULL");
+  *out = nullptr;
+  if (variant != SBD_VARIANT_GENERIC && variant != SBD_VARIANT_PYTHON) return fail(SBD_EINVAL, "bad variant");
+  if (nx < 1 || ny < 1 || nz < 1) return fail(SBD_EDIMS, "nx, ny, nz must be >= 1");  // U:198-201
+  if (variant == SBD_VARIANT_GENERIC && h < 1) return fail(SBD_EINVAL, "generic variant needs halo >= 1");
+  if ((long long)(nx + 2 * h) * (ny + 2 * h) > 0x7fffffffLL) return fail(SBD_EDIMS, "plane too large for 32-bit indexing");
+  int rc = ensure_device();
+  if (rc) return rc;
+  sbd_plan* p = new sbd_plan();
+  p->variant = variant; p->nx = nx; p->ny = ny; p->nz = nz;
+  p->h = (variant == SBD_VARIANT_GENERIC) ? h : 0;
+  p->g = Geo{nx, ny, p->h, nx + 2 * p->h, ny + 2 * p->h};
+  if (prm) p->prm = *prm; else sbd_default_params(&p->prm, variant);
+  cudaError_t e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete p; snprintf(g_err, sizeof g_err, "cudaStreamCreate: %s", cudaGetErrorString(e)); return SBD_ECUDA; }
+  p->stream = p->own_stream;
+  const size_t n = plane_elems(p);
+  if (cudaMalloc((void**)&p->d_gzsm, n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_code, n * sizeof(uint16_t)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_stats, 4 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_carry, 5 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_cnt, 2 * sizeof(int)) != cudaSuccess) {
+    snprintf(g_err, sizeof g_err, "cudaMalloc of plan planes failed: %s", cudaGetErrorString(cudaGetLastError()));
+    sbd_plan_destroy(p);
+    return SBD_ECUDA;
+  }
+  *out = p;
+  return SBD_OK;
+}
+
+void sbd_plan_destroy(sbd_plan* p)
+{
+  if (!p) return;
+  if (p->own_stream) cudaStreamSynchronize(p->own_stream);
+  cudaFree(p->d_gzsm); cudaFree(p->d_code); cudaFree(p->d_stats); cudaFree(p->d_carry); cudaFree(p->d_cnt);
+  for (auto& s : p->stage) cudaFree(s.first);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  delete p;
+}
+
+int sbd_plan_set_stream(sbd_plan* p, void* stream)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  p->stream = stream ? (cudaStream_t)stream : p->own_stream;
+  return SBD_OK;
+}
+void* sbd_plan_get_stream(sbd_plan* p) { return p ? (void*)p->stream : nullptr; }
+int sbd_plan_sync(sbd_plan* p)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  CK(cudaStreamSynchronize(p->stream));
+  return SBD_OK;
+}
+
+int sbd_plan_set_static(sbd_plan* p, const float* mask, const float* z, const float* sigma,
+                        const float* stats_in)
+{
+  if (!p || !mask || !z || !sigma) return fail(SBD_EINVAL, "NULL argument");
+  const size_t n = plane_elems(p);
+  p->stage_used = 0;
+  const float *d_mask, *d_z, *d_sigma;
+  int rc;
+  if ((rc = in_view(p, mask, n, &d_mask))) return rc;
+  if ((rc = in_view(p, z, n, &d_z))) return rc;
+  if ((rc = in_view(p, sigma, n, &d_sigma))) return rc;
+  cudaStream_t st = p->stream;
+  if (stats_in) {
+    float tmp[4] = {stats_in[0], stats_in[1], stats_in[2], 0.0f};
+    CK(cudaMemcpyAsync(p->d_stats, tmp, sizeof tmp, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  } else {
+    // statistics over the interior, sequential order
+    const float* d_int = d_sigma + (size_t)p->h * p->g.ldx + p->h;
+    if ((rc = run_stats(st, d_int, p->nx, p->ny, p->g.ldx, p->d_carry, p->d_stats))) return rc;
+  }
+  const int T = 256;
+  k_static_gzsm<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(d_z, d_sigma, p->d_gzsm, (long long)n, p->d_stats, p->prm.gmma); LAUNCHED();
+  CK(cudaMemsetAsync(p->d_cnt, 0, 2 * sizeof(int), st));
+  dim3 grid(cdiv(p->g.ldx, 128), p->g.ldy);
+  if (p->variant == SBD_VARIANT_GENERIC) {
+    k_static_code<SBD_VARIANT_GENERIC><<<grid, 128, 0, st>>>(d_mask, p->d_code, p->g, p->prm.maxdist,
+                                                            max(p->h, 1), p->ny, p->d_cnt, p->d_cnt + 1);
+  } else {
+    k_static_code<SBD_VARIANT_PYTHON><<<grid, 128, 0, st>>>(d_mask, p->d_code, p->g, p->prm.maxdist,
+                                                           max(p->nx, p->ny), p->ny - 1, p->d_cnt, p->d_cnt + 1);
+  }
+  LAUNCHED();
+  CK(cudaGetLastError());
+  int cnt[2];
+  CK(cudaMemcpyAsync(cnt, p->d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(p->stats, p->d_stats, sizeof p->stats, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  p->nn_max = cnt[0];
+  p->n_coastal = cnt[1];
+  p->R = min(p->nn_max, 16);
+  p->have_static = true;
+  return SBD_OK;
+}
+
+int sbd_plan_info(sbd_plan* p, int* nn_max, int* n_coastal, float* stats4)
+{
+  if (!p || !p->have_static) return fail(SBD_EINVAL, "plan has no static fields yet");
+  if (nn_max) *nn_max = p->nn_max;
+  if (n_coastal) *n_coastal = p->n_coastal;
+  if (stats4) memcpy(stats4, p->stats, sizeof p->stats);
+  return SBD_OK;
+}
+
+static int six_hourly_flag(int step, float timestep_s, float target_time)
+{
+  return sbd_modulo((float)step * timestep_s, target_time) < 0.0001f ? 1 : 0;  // G:264
+}
+
+int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const float* u, const float* v,
+                  const float* theta, float* ws, float* wd, float* thc, float* sb, uint8_t* flags)
+{
+  if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
+  if (!p->have_static) return fail(SBD_EINVAL, "sbd_plan_set_static has not been called");
+  if (!pp || !u || !v || !theta || !ws || !wd || !thc || !sb) return fail(SBD_EINVAL, "NULL argument");
+  const size_t n2 = (size_t)p->nx * p->ny, n3 = n2 * p->nz, nh = plane_elems(p);
+  p->stage_used = 0;
+  std::vector<OutView> pend;
+  TrigArgs a{};
+  int rc;
+  const bool any_host = !is_device_ptr(pp) || !is_device_ptr(theta) || !is_device_ptr(u) || !is_device_ptr(v);
+  if ((rc = in_view(p, pp, n3, &a.p))) return rc;
+  if ((rc = in_view(p, u, n3, &a.u))) return rc;
+  if ((rc = in_view(p, v, n3, &a.v))) return rc;
+  if ((rc = in_view(p, theta, nh, &a.theta))) return rc;
+  const bool first = step < 2;
+  void* d;
+  if ((rc = out_view(p, ws, n2 * 4, true, &d, pend))) return rc; a.ws = (float*)d;
+  if ((rc = out_view(p, wd, n2 * 4, true, &d, pend))) return rc; a.wd = (float*)d;
+  if ((rc = out_view(p, thc, n2 * 4, true, &d, pend))) return rc; a.thc = (float*)d;
+  if ((rc = out_view(p, sb, n2 * 4, false, &d, pend))) return rc; a.sb = (float*)d;
+  if ((rc = out_view(p, flags, n2, false, &d, pend))) return rc; a.flags = (uint8_t*)d;
+  a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny;
+  a.first_step = first ? 1 : 0;
+  a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
+  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
+  return flush_out(p, pend, any_host);
+}
+
+int sbd_plan_step_py(sbd_plan* p, int step, float timestep_min, const float* pp, const float* u,
+                     const float* v, const float* theta, const float* ws, const float* wd, float* output,
+                     uint8_t* flags)
+{
+  if (!p || p->variant != SBD_VARIANT_PYTHON) return fail(SBD_EINVAL, "python plan required");
+  if (!p->have_static) return fail(SBD_EINVAL, "sbd_plan_set_static has not been called");
+  if (!pp || !u || !v || !theta || !ws || !wd || !output) return fail(SBD_EINVAL, "NULL argument");
+  const size_t n2 = (size_t)p->nx * p->ny, n3 = n2 * p->nz;
+  p->stage_used = 0;
+  std::vector<OutView> pend;
+  TrigArgs a{};
+  int rc;
+  const bool any_host = !is_device_ptr(pp) || !is_device_ptr(theta) || !is_device_ptr(u) ||
+                        !is_device_ptr(v) || !is_device_ptr(ws) || !is_device_ptr(wd);
+  if ((rc = in_view(p, pp, p->nz, &a.p))) return rc;
+  // only the selected level of u,v is read, but the level is chosen on the device: stage all
+  if ((rc = in_view(p, u, n3, &a.u))) return rc;
+  if ((rc = in_view(p, v, n3, &a.v))) return rc;
+  if ((rc = in_view(p, theta, n2, &a.theta))) return rc;
+  if ((rc = in_view(p, ws, n2, &a.ws_in))) return rc;
+  if ((rc = in_view(p, wd, n2, &a.wd_in))) return rc;
+  void* d;
+  if ((rc = out_view(p, output, n2 * 4 * 4, false, &d, pend))) return rc; a.out = (float*)d;
+  if ((rc = out_view(p, flags, n2, false, &d, pend))) return rc; a.flags = (uint8_t*)d;
+  a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny - 1;
+  a.first_step = step < 2 ? 1 : 0;
+  a.six_hourly = six_hourly_flag(step, timestep_min * 60.0f, p->prm.target_time);  // P:146, P:271
+  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  if ((rc = launch_trigger<SBD_VARIANT_PYTHON>(p, a))) return rc;
+  return flush_out(p, pend, any_host);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one-shot entry points
+// ---------------------------------------------------------------------------------------------
+int sbd_seabreeze_diag_f32(float timestep, int step, const float* pp, const float* u, const float* v,
+                           const float* theta, const float* mask, const float* z, const float* sigma,
+                           float* ws, float* wd, float* thc, float* sb, int nx, int ny, int nz, int h,
+                           const sbd_params* prm, uint8_t* flags)
+{
+  sbd_plan* p = nullptr;
+  int rc = sbd_plan_create(&p, SBD_VARIANT_GENERIC, nx, ny, nz, h, prm);
+  if (rc) return rc;
+  rc = sbd_plan_set_static(p, mask, z, sigma, nullptr);
+  if (!rc) rc = sbd_plan_step(p, timestep, step, pp, u, v, theta, ws, wd, thc, sb, flags);
+  if (!rc) rc = sbd_plan_sync(p);
+  sbd_plan_destroy(p);
+  return rc;
+}
+
+int sbd_py_diag_f32(int step, const float* pp, const float* z, const float* stdo, const float* theta,
+                    const float* v, const float* u, const float* cdist, const float* ws, const float* wd,
+                    const float* thc, float target_plev, float thresh_wind, float thresh_winddir,
+                    float thresh_windch, float thresh_thc, float target_time, float maxdist,
+                    float timestep, int nps, int nlons, int nlats, float* output, uint8_t* flags)
+{
+  (void)thc;  // never read by the reference (P:268 only assigns it)
+  sbd_params q;
+  sbd_default_params(&q, SBD_VARIANT_PYTHON);
+  q.target_plev = target_plev * 100.0f;         // P:148
+  q.target_time = target_time * (60.0f * 60.0f);  // P:147
+  q.thresh_wind = thresh_wind; q.thresh_winddir = thresh_winddir; q.thresh_windch = thresh_windch;
+  q.thresh_thc = thresh_thc; q.maxdist = maxdist;
+  sbd_plan* p = nullptr;
+  int rc = sbd_plan_create(&p, SBD_VARIANT_PYTHON, nlons, nlats, nps, 0, &q);
+  if (rc) return rc;
+  rc = sbd_plan_set_static(p, cdist, z, stdo, nullptr);
+  if (!rc) rc = sbd_plan_step_py(p, step, timestep, pp, u, v, theta, ws, wd, output, flags);
+  if (!rc) rc = sbd_plan_sync(p);
+  sbd_plan_destroy(p);
+  return rc;
+}
+
+int sbd_get_edges_f32(float* mask, const float* ice, const float* land, int nx, int ny, int h, int swap,
+                      uint8_t* m1)
+{
+  if (!mask || !ice || !land) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  if (h < 1) return fail(SBD_EINVAL, "halo must be >= 1");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  const size_t n2 = (size_t)nx * ny, nh = (size_t)(nx + 2 * h) * (ny + 2 * h);
+  const float *d_ice, *d_land;
+  void *d_mask, *d_m1, *d_coast;
+  if ((rc = t.in(ice, n2, &d_ice))) return rc;
+  if ((rc = t.in(land, n2, &d_land))) return rc;
+  if ((rc = t.out(mask, nh * 4, true, &d_mask))) return rc;  // halos may be caller-initialised (swap==0)
+  if ((rc = t.out(m1, n2, false, &d_m1))) return rc;
+  if ((rc = t.scratch(n2 * 4, &d_coast))) return rc;
+  dim3 g(cdiv(nx, 128), ny);
+  k_binarise_generic<<<g, 128, 0, t.st>>>((float*)d_mask, d_ice, d_land, nx, ny, h, (uint8_t*)d_m1); LAUNCHED();
+  if (swap && (rc = swap_bounds_dev(t.st, (float*)d_mask, nx, ny, h, true))) return rc;   // G:342
+  k_sobel_generic<<<g, 128, 0, t.st>>>((const float*)d_mask, (float*)d_coast, nx, ny, h); LAUNCHED();
+  k_copy_interior<<<g, 128, 0, t.st>>>((float*)d_mask, (const float*)d_coast, nx, ny, h); LAUNCHED();  // G:369
+  if (swap && (rc = swap_bounds_dev(t.st, (float*)d_mask, nx, ny, h, true))) return rc;   // G:371
+  CK(cudaGetLastError());
+  return t.finish();
+}
+
+int sbd_swap_bounds_f32(float* field, int nx, int ny, int h)
+{
+  if (!field || nx < 1 || ny < 1 || h < 0) return fail(SBD_EINVAL, "bad argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  void* d;
+  if ((rc = t.out(field, (size_t)(nx + 2 * h) * (ny + 2 * h) * 4, true, &d))) return rc;
+  if ((rc = swap_bounds_dev(t.st, (float*)d, nx, ny, h, true))) return rc;
+  return t.finish();
+}
+int sbd_swap_bounds_ew_f32(float* field, int nx, int ny, int h)
+{
+  if (!field || nx < 1 || ny < 1 || h < 0) return fail(SBD_EINVAL, "bad argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  void* d;
+  if ((rc = t.out(field, (size_t)(nx + 2 * h) * (ny + 2 * h) * 4, true, &d))) return rc;
+  if ((rc = swap_bounds_dev(t.st, (float*)d, nx, ny, h, false))) return rc;
+  return t.finish();
+}
+
+int sbd_py_get_edges_f32(const float* lsm, const float* ci, int nlons, int nlats, float* coast)
+{
+  if (!lsm || !ci || !coast) return fail(SBD_EINVAL, "NULL argument");
+  if (nlons < 1 || nlats < 1) return fail(SBD_EDIMS, "bad dims");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  const size_t n2 = (size_t)nlons * nlats;
+  const float *d_lsm, *d_ci;
+  void* d_coast;
+  if ((rc = t.in(lsm, n2, &d_lsm))) return rc;
+  if ((rc = t.in(ci, n2, &d_ci))) return rc;
+  if ((rc = t.out(coast, n2 * 4, false, &d_coast))) return rc;
+  dim3 g(cdiv(nlons, 128), nlats);
+  k_edges_py<<<g, 128, 0, t.st>>>(d_lsm, d_ci, (float*)d_coast, nlons, nlats); LAUNCHED();
+  CK(cudaGetLastError());
+  return t.finish();
+}
+
+static int dist_common(const float* coast, int coast_ld, int coast_off, size_t coast_elems,
+                       const float* land, const float* lon, const float* lat, int nx, int ny,
+                       float maxdist, int k, float* cdist, int* k_out)
+{
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  const size_t n2 = (size_t)nx * ny;
+  const float *d_coast, *d_land, *d_lon, *d_lat;
+  void* d_cdist;
+  if ((rc = t.in(coast, coast_elems, &d_coast))) return rc;
+  if ((rc = t.in(land, n2, &d_land))) return rc;
+  if ((rc = t.in(lon, nx, &d_lon))) return rc;
+  if ((rc = t.in(lat, ny, &d_lat))) return rc;
+  if ((rc = t.out(cdist, n2 * 4, false, &d_cdist))) return rc;
+  if (k < 0) {
+    void* d_k;
+    if ((rc = t.scratch(sizeof(int), &d_k))) return rc;
+    k_dist_radius<<<1, 1, 0, t.st>>>(d_lon, d_lat, nx, ny, maxdist, (int*)d_k); LAUNCHED();
+    CK(cudaMemcpyAsync(&k, d_k, sizeof(int), cudaMemcpyDeviceToHost, t.st));
+    CK(cudaStreamSynchronize(t.st));
+    if (k < 0) return fail(SBD_EINVAL, "get_dist: cannot derive the search radius (70-degree row is the last row, or nlons < 2)");
+  }
+  if (k_out) *k_out = k;
+  if ((rc = dist_dev(t.st, d_coast, coast_ld, coast_off, d_land, d_lon, d_lat, nx, ny, k, maxdist, (float*)d_cdist))) return rc;
+  return t.finish();
+}
+
+int sbd_py_get_dist_f32(const float* coast, const float* mask, const float* lon, const float* lat,
+                        int nlons, int nlats, float maxdist, float* cdist, int* k_out)
+{
+  if (!coast || !mask || !lon || !lat || !cdist) return fail(SBD_EINVAL, "NULL argument");
+  if (nlons < 2 || nlats < 2) return fail(SBD_EDIMS, "bad dims");
+  return dist_common(coast, nlons, 0, (size_t)nlons * nlats, mask, lon, lat, nlons, nlats, maxdist, -1, cdist, k_out);
+}
+
+int sbd_get_dist_f32(const float* coast, const float* land, const float* lon, const float* lat,
+                     float maxdist, float* cdist, int nx, int ny, int h)
+{
+  if (!coast || !land || !lon || !lat || !cdist) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  if (h < 0) return fail(SBD_EINVAL, "bad halo");
+  const int ldx = nx + 2 * h;
+  return dist_common(coast, ldx, h * ldx + h, (size_t)ldx * (ny + 2 * h), land, lon, lat, nx, ny, maxdist, h, cdist, nullptr);
+}
+
+int sbd_sigmoid_f32(const float* ary, float* sm, int nx, int ny, float* stats)
+{
+  if (!ary) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  const size_t n2 = (size_t)nx * ny;
+  const float* d_ary;
+  void *d_sm, *d_carry, *d_stats;
+  if ((rc = t.in(ary, n2, &d_ary))) return rc;
+  if ((rc = t.out(sm, n2 * 4, false, &d_sm))) return rc;
+  if ((rc = t.scratch(5 * 4, &d_carry))) return rc;
+  if ((rc = t.scratch(4 * 4, &d_stats))) return rc;
+  if ((rc = run_stats(t.st, d_ary, nx, ny, nx, (float*)d_carry, (float*)d_stats))) return rc;
+  if (d_sm) {
+    k_sigmoid_apply<<<(unsigned)((n2 + 255) / 256), 256, 0, t.st>>>(d_ary, (float*)d_sm, (long long)n2, (const float*)d_stats); LAUNCHED();
+  }
+  CK(cudaGetLastError());
+  if (stats) CK(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, t.st));
+  return t.finish();
+}
+int sbd_py_sigmoid_f32(const float* ary, int nlons, int nlats, float* sm)
+{
+  return sbd_sigmoid_f32(ary, sm, nlons, nlats, nullptr);
+}
+
+int sbd_stats_chain_f32(const float* ary, int nx, int ny, int ld, int pass, int first, float* carry5)
+{
+  if (!ary || !carry5) return fail(SBD_EINVAL, "NULL argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  const float* d_ary;
+  void* d_carry;
+  if ((rc = t.in(ary, (size_t)ld * (ny - 1) + nx, &d_ary))) return rc;
+  if ((rc = t.scratch(5 * 4, &d_carry))) return rc;
+  CK(cudaMemcpyAsync(d_carry, carry5, 20, cudaMemcpyHostToDevice, t.st));
+  k_stats_seq<<<1, 32, 0, t.st>>>(d_ary, nx, ny, ld, pass, first, (float*)d_carry); LAUNCHED();
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(carry5, d_carry, 20, cudaMemcpyDeviceToHost, t.st));
+  return t.finish();
+}
+
+}  // extern "C"

@@ -102,6 +102,9 @@ int sbd_seabreeze_diag_f32(float timestep, int timestep_number, const float* p, 
  * periodic part. */
 int sbd_swap_bounds_f32(float* field, int nx, int ny, int h);
 int sbd_swap_bounds_ew_f32(float* field, int nx, int ny, int h);
+/* Asynchronous device-only form: one kernel on `stream` (cudaStream_t as void*).  ns_mask bit0 /
+ * bit1: replicate the top / bottom edge rows (clear the bit for a side owned by a neighbour rank). */
+int sbd_swap_bounds_dev_f32(float* d_field, int nx, int ny, int h, int ns_mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Python (f2py module `seabreeze`) entry points: same positional meaning as the f2py signatures.
@@ -143,8 +146,10 @@ typedef struct sbd_plan sbd_plan;
  * python.  prm may be NULL (defaults of the variant). */
 int sbd_plan_create(sbd_plan** plan, int variant, int nx, int ny, int nz, int h, const sbd_params* prm);
 void sbd_plan_destroy(sbd_plan* plan);
-/* Use an external CUDA stream (cudaStream_t cast to void*); NULL restores the plan's own. */
+/* Use an external CUDA stream (cudaStream_t cast to void*); NULL is the legacy default stream.
+ * sbd_plan_use_own_stream restores the plan's own non-blocking stream. */
 int sbd_plan_set_stream(sbd_plan* plan, void* stream);
+int sbd_plan_use_own_stream(sbd_plan* plan);
 void* sbd_plan_get_stream(sbd_plan* plan);
 int sbd_plan_sync(sbd_plan* plan);
 
@@ -166,6 +171,13 @@ int sbd_plan_step(sbd_plan* plan, float timestep, int timestep_number, const flo
 int sbd_plan_step_py(sbd_plan* plan, int timestep_number, float timestep_min, const float* p,
                      const float* u, const float* v, const float* theta, const float* windspeed,
                      const float* winddir, float* output, uint8_t* flags);
+/* Per-kernel CUDA-event timing of the step (off by default), events recorded on the stream the
+ * kernels are launched on.  While timing is on the two kernels of the generic step run strictly
+ * one after the other (no programmatic dependent launch), so each duration is that kernel alone:
+ * ms3[0] = window / thermal-contrast kernel (k_trigger), ms3[1] = level-scan + trigger kernel
+ * (k_scan_quad), ms3[2] = 0 (reserved).  Python variant: one kernel, ms3[1] = 0. */
+int sbd_plan_set_timing(sbd_plan* plan, int on);
+int sbd_plan_last_timing(sbd_plan* plan, float* ms3);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 unsigned long long sbd_launch_count(void);
 

@@ -16,12 +16,12 @@ SBD_VARIANT_PYTHON = 1
 SYMBOLS = [
     "sbd_default_params", "sbd_last_error", "sbd_device_count",
     "sbd_get_edges_f32", "sbd_get_dist_f32", "sbd_sigmoid_f32", "sbd_seabreeze_diag_f32",
-    "sbd_swap_bounds_f32", "sbd_swap_bounds_ew_f32",
+    "sbd_swap_bounds_f32", "sbd_swap_bounds_ew_f32", "sbd_swap_bounds_dev_f32",
     "sbd_py_get_edges_f32", "sbd_py_get_dist_f32", "sbd_py_sigmoid_f32", "sbd_py_diag_f32",
     "sbd_get_threads",
-    "sbd_plan_create", "sbd_plan_destroy", "sbd_plan_set_stream", "sbd_plan_get_stream",
+    "sbd_plan_create", "sbd_plan_destroy", "sbd_plan_set_stream", "sbd_plan_use_own_stream", "sbd_plan_get_stream",
     "sbd_plan_sync", "sbd_plan_set_static", "sbd_plan_info", "sbd_plan_step", "sbd_plan_step_py",
-    "sbd_launch_count", "sbd_stats_chain_f32",
+    "sbd_launch_count", "sbd_stats_chain_f32", "sbd_plan_set_timing", "sbd_plan_last_timing",
 ]
 
 
@@ -71,6 +71,7 @@ def load():
                                            C.POINTER(SbdParams), vp]
     lib.sbd_swap_bounds_f32.argtypes = [fp, i, i, i]
     lib.sbd_swap_bounds_ew_f32.argtypes = [fp, i, i, i]
+    lib.sbd_swap_bounds_dev_f32.argtypes = [fp, i, i, i, i, vp]
     lib.sbd_py_get_edges_f32.argtypes = [fp, fp, i, i, fp]
     lib.sbd_py_get_dist_f32.argtypes = [fp, fp, fp, fp, i, i, f, fp, ip]
     lib.sbd_py_sigmoid_f32.argtypes = [fp, i, i, fp]
@@ -80,6 +81,7 @@ def load():
     lib.sbd_plan_destroy.argtypes = [vp]
     lib.sbd_plan_destroy.restype = None
     lib.sbd_plan_set_stream.argtypes = [vp, vp]
+    lib.sbd_plan_use_own_stream.argtypes = [vp]
     lib.sbd_plan_get_stream.argtypes = [vp]
     lib.sbd_plan_get_stream.restype = vp
     lib.sbd_plan_sync.argtypes = [vp]
@@ -87,6 +89,8 @@ def load():
     lib.sbd_plan_info.argtypes = [vp, ip, ip, fp]
     lib.sbd_plan_step.argtypes = [vp, f, i, fp, fp, fp, fp, fp, fp, fp, fp, vp]
     lib.sbd_plan_step_py.argtypes = [vp, i, f, fp, fp, fp, fp, fp, fp, fp, vp]
+    lib.sbd_plan_set_timing.argtypes = [vp, i]
+    lib.sbd_plan_last_timing.argtypes = [vp, fp]
     lib.sbd_stats_chain_f32.argtypes = [fp, i, i, i, i, i, fp]
     _LIB = lib
     return lib

@@ -9,8 +9,11 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA contraction: the
 // reference arithmetic has separate multiplies and adds; include/sbd_math.h relies on it too).
 #include <cuda_runtime.h>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <atomic>
@@ -181,6 +184,33 @@ __global__ void k_halo_ns(float* __restrict__ f, int nx, int ny, int h)
   if (x >= ldx) return;
   if (t < h) f[(size_t)t * ldx + x] = f[(size_t)h * ldx + x];
   else f[(size_t)(ny + h + (t - h)) * ldx + x] = f[(size_t)(ny + h - 1) * ldx + x];
+}
+
+// one-launch halo fill straight from interior values: east-west periodic on all rows, north-south
+// edge replication for the sides selected by ns_mask (bit0 = top rows, bit1 = bottom rows; a side
+// owned by a neighbouring rank is left for the NCCL exchange).
+__global__ void k_halo_all(float* __restrict__ f, int nx, int ny, int h, int ns_mask)
+{
+  const int ldx = nx + 2 * h;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_ns = 2LL * h * ldx, n_ew = 2LL * h * ny;
+  int px, py;
+  if (t < n_ns) {
+    const int r = (int)(t / ldx);
+    px = (int)(t % ldx);
+    if (r < h) { if (!(ns_mask & 1)) return; py = r; }
+    else { if (!(ns_mask & 2)) return; py = ny + h + (r - h); }
+  } else if (t < n_ns + n_ew) {
+    const long long q = t - n_ns;
+    py = h + (int)(q / (2 * h));
+    const int c = (int)(q % (2 * h));
+    px = (c < h) ? c : nx + h + (c - h);
+  } else {
+    return;
+  }
+  int sx = (px - h) % nx; if (sx < 0) sx += nx;
+  const int sy = min(max(py - h, 0), ny - 1);
+  f[(size_t)py * ldx + px] = f[(size_t)(sy + h) * ldx + (sx + h)];
 }
 
 // python get_edges (S:58-88): mask = (lsm+ci) > 0.4 evaluated at neighbour-read time.
@@ -522,23 +552,143 @@ __device__ __forceinline__ void window_sums_global(const TrigArgs& a, int gx, in
     }
 }
 
-template <int VARIANT, int TX, int TY, int NT>
+// wind speed and direction at the selected level (G:225-227)
+__device__ __forceinline__ void wind_from_uv(const TrigArgs& a, float uu, float vv, float& n_ws, float& n_wd)
+{
+  n_ws = sqrtf(uu * uu + vv * vv);                            // G:225
+  n_wd = sbd_atan2f(-1.0f * uu, -1.0f * vv) * a.prm.rad2deg;  // G:227
+}
+
+// Per-cell threshold logic shared by every variant (G:235-266 == P:236-274).
+//   generic: reads the previous windspeed / winddir from a.ws / a.wd, writes sb, ws, wd, flags.
+//   python : previous state comes in as ws_prev / wd_prev, results go to the 4-plane output.
+template <int VARIANT>
+__device__ __forceinline__ void trigger_point(const TrigArgs& a, size_t c, size_t n2, float n_thc, float n_ws,
+                                              float n_wd, float t0_own)
+{
+  float ws, wd;
+  if (a.first_step) { ws = n_ws; wd = n_wd; }                             // G:235-239
+  else if (VARIANT == SBD_VARIANT_GENERIC) { ws = a.ws[c]; wd = a.wd[c]; }
+  else { ws = a.ws_in[c]; wd = a.wd_in[c]; }
+  const float thc_abs = fabsf(n_thc);                                     // G:242
+  const float mws = (ws + n_ws) / 2.0f;                                   // G:243
+  const float dws = fabsf(ws - n_ws);                                     // G:244
+  const float dwd = fabsf(sbd_modulo((wd - n_wd) + 180.0f, 360.0f) - 180.0f);  // G:246-247
+  float sb = 0.0f;                                                        // G:258
+  uint8_t fl = 1;
+  if (dwd < a.prm.thresh_winddir && dws < a.prm.thresh_windch && mws < a.prm.thresh_wind &&
+      thc_abs > a.prm.thresh_thc) {                                       // G:249-252
+    const float scale_wind = (a.prm.thresh_wind - mws) / fmaxf(1.0f, mws);  // G:254
+    const float scale_thc = (thc_abs - a.prm.thresh_thc) / n_thc;           // G:255
+    sb = scale_thc * scale_wind;                                             // G:256
+    fl = 3;
+  }
+  if (VARIANT == SBD_VARIANT_GENERIC) {
+    a.sb[c] = sb;
+    a.ws[c] = n_ws;                                                       // G:261
+    if (a.six_hourly || a.first_step) a.wd[c] = n_wd;                     // G:237, G:264-266
+  } else {
+    if (a.six_hourly) { ws = n_ws; wd = n_wd; }                           // P:271-274
+    a.out[c] = sb;                                                        // P:277
+    a.out[n2 + c] = t0_own;                                               // P:278
+    a.out[2 * n2 + c] = ws;                                               // P:279
+    a.out[3 * n2 + c] = wd;                                               // P:280
+  }
+  if (a.flags) a.flags[c] = fl;
+}
+
+// generic-variant thresholds with the previous windspeed / winddir already in registers
+__device__ __forceinline__ void trigger_point_vals(const TrigArgs& a, size_t c, float n_thc, float n_ws,
+                                                   float n_wd, float ws_prev, float wd_prev)
+{
+  float ws = ws_prev, wd = wd_prev;
+  if (a.first_step) { ws = n_ws; wd = n_wd; }                             // G:235-239
+  const float thc_abs = fabsf(n_thc);                                     // G:242
+  const float mws = (ws + n_ws) / 2.0f;                                   // G:243
+  const float dws = fabsf(ws - n_ws);                                     // G:244
+  const float dwd = fabsf(sbd_modulo((wd - n_wd) + 180.0f, 360.0f) - 180.0f);  // G:246-247
+  float sb = 0.0f;                                                        // G:258
+  uint8_t fl = 1;
+  if (dwd < a.prm.thresh_winddir && dws < a.prm.thresh_windch && mws < a.prm.thresh_wind &&
+      thc_abs > a.prm.thresh_thc) {                                       // G:249-252
+    const float scale_wind = (a.prm.thresh_wind - mws) / fmaxf(1.0f, mws);  // G:254
+    const float scale_thc = (thc_abs - a.prm.thresh_thc) / n_thc;           // G:255
+    sb = scale_thc * scale_wind;                                             // G:256
+    fl = 3;
+  }
+  a.sb[c] = sb;
+  a.ws[c] = n_ws;                                                         // G:261
+  if (a.six_hourly || a.first_step) a.wd[c] = n_wd;                       // G:237, G:264-266
+  if (a.flags) a.flags[c] = fl;
+}
+
+// Sequential raster sum over a (2NN+1)^2 window held in shared memory, row length known at compile
+// time: per element one LDS and one predicated FADD pair (G:198-208 order).  s_bits holds the land
+// bit of every staged cell, rows padded to WBITS bits.
+template <int NN>
+__device__ __forceinline__ void window_fixed(const float* __restrict__ s_t0, const uint32_t* __restrict__ s_bits,
+                                             int W, int WBITS, int lcx, int lcy, float& T_l, float& T_s,
+                                             uint32_t& c_l)
+{
+  constexpr int WL = 2 * NN + 1;
+#pragma unroll 1
+  for (int r = 0; r < WL; ++r) {
+    const int ii = lcy - NN + r;
+    const int bpos = ii * WBITS + lcx - NN;
+    uint32_t bits = __funnelshift_r(s_bits[bpos >> 5], s_bits[(bpos >> 5) + 1], bpos & 31);
+    bits &= (WL < 32) ? ((1u << WL) - 1u) : 0xffffffffu;
+    c_l += __popc(bits);
+    const float* tp = s_t0 + ii * W + lcx - NN;
+#pragma unroll
+    for (int j = 0; j < WL; ++j) {
+      const float t = tp[j];
+      if (bits & (1u << j)) T_l = T_l + t;   // G:200-202
+      else T_s = T_s + t;                    // G:204-205
+    }
+  }
+}
+
+// K4a window kernel.
+//   phase 1  stage t0 = theta - gzsm (G:167) and the land bit of the tile + halo R in shared memory
+//   phase 2  every thread classifies its cells; coastal-zone cells go into a shared work list
+//            bucketed by their (static) final search radius nn, so that the lanes of a warp sum
+//            windows of equal size; cells outside the zone get their sb_con right away
+//   phase 3  one list entry per thread at a time: sequential raster sum over the final
+//            (2nn+1)^2 window -- bit-identical to the last pass of the reference's growing
+//            search (G:191-214) -- then n_thc (G:216)
+//   SPLIT (generic): n_thc is stored to thc[] (state update G:262); level search + thresholds
+//            run in k_scan_quad / k_final.  Otherwise (python: one global level) the thresholds
+//            are applied here.
+template <int VARIANT, int TX, int TY, int NT, bool SPLIT>
 __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
 {
-  constexpr int CPT = TX * TY / NT;  // cells per thread
+  constexpr int CPT = TX * TY / NT;  // cells per thread in phase 2
+  constexpr int NB = 64;             // nn buckets: 1..NB-2 exact, NB-1 = "wider than the tile halo"
   static_assert(TX % 32 == 0 && NT % TX == 0 && (TX * TY) % NT == 0, "tile shape");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = a.R;
   const int W = TX + 2 * R, Hh = TY + 2 * R;
+  const int total = W * Hh;
+  const int WBW = (W + 31) >> 5, WBITS = WBW * 32;  // land bits: rows padded to whole words
   float* s_t0 = reinterpret_cast<float*>(smem_raw);
-  uint8_t* s_land = reinterpret_cast<uint8_t*>(s_t0 + W * Hh);
+  // land/sea sign of every staged cell (bit ly*WBITS + lx), two pad words at the end so that the
+  // two-word funnel reads never run off the array
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_t0 + total);
+  uint32_t* s_list = s_bits + Hh * WBW + 2;  // TX*TY entries: land << 31 | bucket << 16 | local cell id
+  __shared__ int s_cnt[NB];
+  __shared__ int s_off[NB];
   __shared__ int s_lev;
 
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int tid = threadIdx.x;
 
+  // programmatic dependent launch: let the level-scan kernel that follows in the stream start
+  // right away; it waits (griddepcontrol.wait) only before it consumes n_thc
+  if (SPLIT) asm volatile("griddepcontrol.launch_dependents;");
+
+  if (tid < NB) s_cnt[tid] = 0;
   // ---- python: one pressure level for the whole grid (P:228), first minimum of |p - target| ----
-  if (VARIANT == SBD_VARIANT_PYTHON && tid == 0) {
+  if (VARIANT == SBD_VARIANT_PYTHON && tid == NT - 1) {
     int lev = 0;
     float best = fabsf(a.p[0] - a.prm.target_plev);
     for (int k = 1; k < a.nz; ++k) {
@@ -548,150 +698,372 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
     s_lev = lev;
   }
 
-  // ---- phase 1: stage t0 and the land bit for the tile + halo ----
-  for (int idx = tid; idx < W * Hh; idx += NT) {
-    const int ly = idx / W, lx = idx - ly * W;
-    const int s = nbr_index<VARIANT>(a.g, x0 - R + lx, y0 - R + ly);
-    s_t0[idx] = a.theta[s] - a.gzsm[s];  // G:167
-    s_land[idx] = (uint8_t)(a.code[s] >> 15);
+  // ---- phase 1 ----  one warp per staged row, all loads of a row in flight together
+  {
+    constexpr int MAXC = (TX + 2 * 16 + 31) / 32;  // R <= 16 for this tile shape
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int ly = warp; ly < Hh; ly += NT / 32) {
+      float th[MAXC], gz[MAXC];
+      uint32_t cd[MAXC];
+#pragma unroll
+      for (int cch = 0; cch < MAXC; ++cch) {
+        const int lx = cch * 32 + lane;
+        th[cch] = 0.0f; gz[cch] = 0.0f; cd[cch] = 0u;
+        if (lx < W) {
+          const int sidx = nbr_index<VARIANT>(a.g, x0 - R + lx, y0 - R + ly);
+          th[cch] = a.theta[sidx];
+          gz[cch] = a.gzsm[sidx];
+          cd[cch] = a.code[sidx];
+        }
+      }
+#pragma unroll
+      for (int cch = 0; cch < MAXC; ++cch) {
+        const int lx = cch * 32 + lane;
+        if (lx < W) s_t0[ly * W + lx] = th[cch] - gz[cch];  // G:167
+        const uint32_t bb = __ballot_sync(0xffffffffu, (cd[cch] >> 15) != 0);
+        if (lane == 0 && cch * 32 < WBITS) s_bits[ly * WBW + cch] = bb;
+      }
+    }
+    if (tid < 2) s_bits[Hh * WBW + tid] = 0u;
   }
   __syncthreads();
 
+  // ---- phase 2 ----
   const int cx = tid % TX;
   const int cy0 = (tid / TX) * CPT;
   const size_t n2 = (size_t)a.g.nx * a.g.ny;
-
-  float n_thc[CPT];
-  bool active[CPT];   // coastal zone & processed
-  bool inside[CPT];
+  uint32_t my_code[CPT];
+  int my_slot[CPT];
 #pragma unroll
   for (int q = 0; q < CPT; ++q) {
     const int gx = x0 + cx, gy = y0 + cy0 + q;
-    inside[q] = gx < a.g.nx && gy < a.g.ny;
-    active[q] = false;
-    n_thc[q] = 0.0f;
-    if (!inside[q]) continue;
-    const uint32_t cd = a.code[own_index<VARIANT>(a.g, gx, gy)];
+    my_code[q] = 0;
+    my_slot[q] = -1;
+    if (gx >= a.g.nx || gy >= a.g.ny) continue;
+    const int so = own_index<VARIANT>(a.g, gx, gy);
+    const uint32_t cd = a.code[so];
     const int nn = (int)(cd & 0x7fffu);
-    if (nn == 0) continue;
-    active[q] = true;
+    my_code[q] = cd;
+    const size_t c = (size_t)gy * a.g.nx + gx;
+    if (nn == 0) {  // outside the coastal zone (G:174-176) or not processed (P:165)
+      if (VARIANT == SBD_VARIANT_GENERIC) {
+        a.sb[c] = a.prm.missing;
+      } else {
+        a.out[c] = a.prm.missing;                   // P:173
+        a.out[n2 + c] = a.theta[so] - a.gzsm[so];   // P:278
+        a.out[2 * n2 + c] = a.ws_in[c];             // P:279
+        a.out[3 * n2 + c] = a.wd_in[c];             // P:280
+      }
+      if (a.flags) a.flags[c] = 0;
+    } else {
+      const int bkt = (nn <= R && nn < NB - 1) ? nn : NB - 1;
+      my_slot[q] = atomicAdd(&s_cnt[bkt], 1);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < NB; ++k) { s_off[k] = run; run += s_cnt[k]; }
+  }
+  __syncthreads();
+  int n_list = 0;
+#pragma unroll
+  for (int q = 0; q < CPT; ++q) {
+    if (my_slot[q] >= 0) {
+      const int nn = (int)(my_code[q] & 0x7fffu);
+      const int bkt = (nn <= R && nn < NB - 1) ? nn : NB - 1;
+      const int lid = (cy0 + q) * TX + cx;
+      s_list[s_off[bkt] + my_slot[q]] = ((my_code[q] & 0x8000u) << 16) | ((uint32_t)bkt << 16) | (uint32_t)lid;
+    }
+  }
+  __syncthreads();
+  n_list = s_off[NB - 1] + s_cnt[NB - 1];
+
+  // ---- phase 3 ----
+  for (int e = tid; e < n_list; e += NT) {
+    const uint32_t ent = s_list[e];
+    const int lid = (int)(ent & 0xffffu);
+    const int ly = lid / TX, lx = lid - ly * TX;
+    const int gx = x0 + lx, gy = y0 + ly;
+    const int so = own_index<VARIANT>(a.g, gx, gy);
+    const int bkt = (int)((ent >> 16) & 0x7fffu);
+    const bool land_c = (ent >> 31) != 0;
+    int nn = bkt;
     float T_l = 0.0f, T_s = 0.0f;
     uint32_t c_l = 0, c_s = 0;
-    if (nn <= R) {
-      const int lcx = R + cx, lcy = R + cy0 + q;
-      for (int ii = lcy - nn; ii <= lcy + nn; ++ii) {
-        const float* tr = s_t0 + ii * W;
-        const uint8_t* lr = s_land + ii * W;
-        for (int jj = lcx - nn; jj <= lcx + nn; ++jj) {
-          const float t = tr[jj];
-          if (lr[jj]) { T_l = T_l + t; ++c_l; }   // G:200-202
-          else { T_s = T_s + t; ++c_s; }          // G:204-205
+    if (bkt != NB - 1) {
+      const int lcx = R + lx, lcy = R + ly;
+      switch (nn) {
+        case 1: window_fixed<1>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+        case 2: window_fixed<2>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+        case 3: window_fixed<3>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+        case 4: window_fixed<4>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+        case 5: window_fixed<5>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+        case 6: window_fixed<6>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+        case 7: window_fixed<7>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+        case 8: window_fixed<8>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+        default: {
+          const int wlen = 2 * nn + 1;
+          for (int ii = lcy - nn; ii <= lcy + nn; ++ii) {
+            int bpos = ii * WBITS + lcx - nn;
+            const float* tp = s_t0 + ii * W + lcx - nn;
+            int rem = wlen;
+            while (rem > 0) {
+              const int cnt = min(rem, 32);
+              uint32_t bits = __funnelshift_r(s_bits[bpos >> 5], s_bits[(bpos >> 5) + 1], bpos & 31);
+              if (cnt < 32) bits &= (1u << cnt) - 1u;
+              c_l += __popc(bits);
+#pragma unroll 4
+              for (int j = 0; j < cnt; ++j) {
+                const float t = tp[j];
+                if (bits & 1u) T_l = T_l + t;   // G:200-202
+                else T_s = T_s + t;             // G:204-205
+                bits >>= 1;
+              }
+              bpos += cnt; tp += cnt; rem -= cnt;
+            }
+          }
         }
       }
+      const int wl = 2 * nn + 1;
+      c_s = (uint32_t)(wl * wl) - c_l;
     } else {
+      nn = (int)(a.code[so] & 0x7fffu);
       window_sums_global<VARIANT>(a, gx, gy, nn, T_l, T_s, c_l, c_s);
     }
     // n_l, n_s are fp32 counters in the reference: n = n + 1 saturates at 2^24
     const float n_l = (float)min(c_l, 16777216u), n_s = (float)min(c_s, 16777216u);
-    const float mul = (cd & 0x8000u) ? 1.0f : -1.0f;        // G:182-186
-    n_thc[q] = mul * ((T_l / n_l) - (T_s / n_s));            // G:216
-  }
-
-  // ---- phase 2: pressure level, wind, thresholds, state ----
-  int lev[CPT];
-  if (VARIANT == SBD_VARIANT_GENERIC) {
-    float best[CPT];
-    const float tp = a.prm.target_plev;
-#pragma unroll
-    for (int q = 0; q < CPT; ++q) { lev[q] = 0; best[q] = __int_as_float(0x7f800000); }
-    if (a.prm.level_scan == 0) {
-      // minloc(abs(p(j,i,:) - target_plev)), first minimum (G:223)
-#pragma unroll 4
-      for (int k = 0; k < a.nz; ++k) {
-#pragma unroll
-        for (int q = 0; q < CPT; ++q) {
-          if (active[q]) {
-            const size_t c = (size_t)(y0 + cy0 + q) * a.g.nx + (x0 + cx);
-            const float d = fabsf(__ldg(a.p + (size_t)k * n2 + c) - tp);
-            if (k == 0 || d < best[q]) { best[q] = d; lev[q] = k; }
-          }
-        }
-      }
+    const float mul = land_c ? 1.0f : -1.0f;                    // G:182-186
+    const float n_thc = mul * ((T_l / n_l) - (T_s / n_s));      // G:216
+    const size_t c = (size_t)gy * a.g.nx + gx;
+    if (SPLIT) {
+      a.thc[c] = n_thc;                                         // G:262
+    } else if (VARIANT == SBD_VARIANT_PYTHON) {
+      const int lev = s_lev;
+      const float uu = __ldg(a.u + (size_t)lev * n2 + c), vv = __ldg(a.v + (size_t)lev * n2 + c);
+      float n_ws, n_wd;
+      wind_from_uv(a, uu, vv, n_ws, n_wd);
+      trigger_point<VARIANT>(a, c, n2, n_thc, n_ws, n_wd, a.theta[so] - a.gzsm[so]);
     } else {
-      // early-exit scan with <= (U:265-274)
-#pragma unroll
-      for (int q = 0; q < CPT; ++q) {
-        if (!active[q]) continue;
-        const size_t c = (size_t)(y0 + cy0 + q) * a.g.nx + (x0 + cx);
+      // generic, unsplit: per-cell level search (G:223 / U:265-274)
+      const float tp = a.prm.target_plev;
+      int lev = 0;
+      if (a.prm.level_scan == 0) {
+        float best = 0.0f;
+        for (int k = 0; k < a.nz; ++k) {
+          const float d = fabsf(__ldg(a.p + (size_t)k * n2 + c) - tp);
+          if (k == 0 || d < best) { best = d; lev = k; }
+        }
+      } else {
         float diff = 1000000.0f;
         for (int k = 0; k < a.nz; ++k) {
           const float d = fabsf(__ldg(a.p + (size_t)k * n2 + c) - tp);
-          if (d <= diff) { lev[q] = k; diff = d; } else break;
+          if (d <= diff) { lev = k; diff = d; } else break;
         }
+      }
+      const float uu = __ldg(a.u + (size_t)lev * n2 + c), vv = __ldg(a.v + (size_t)lev * n2 + c);
+      float n_ws, n_wd;
+      wind_from_uv(a, uu, vv, n_ws, n_wd);
+      a.thc[c] = n_thc;
+      trigger_point<VARIANT>(a, c, n2, n_thc, n_ws, n_wd, 0.0f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b scan+trigger (generic variant): one thread per coastal-zone cell of the compacted, raster-
+// ordered list idx[].  Streams the cell's pressure column (nz levels, stride nx*ny) with BATCH
+// independent loads in flight per thread, finds the first minimum of |p - target_plev| (G:223),
+// then wind, thresholds, scaling and state update (G:225-266).  n_thc was written to thc[] by
+// k_trigger<SPLIT>.
+// ------------------------------------------------------------------------------------------------
+template <int BATCH>
+__global__ void __launch_bounds__(256) k_scan_trigger(const TrigArgs a, const int* __restrict__ idx,
+                                                      int n_active)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_active) return;
+  const int c = idx[i];
+  const size_t n2 = (size_t)a.g.nx * a.g.ny;
+  const float tp = a.prm.target_plev;
+  const float* pc = a.p + c;
+  const int nz = a.nz;
+  int lev = 0;
+  if (a.prm.level_scan == 0) {
+    float best = __int_as_float(0x7f800000);
+    for (int k0 = 0; k0 < nz; k0 += BATCH) {
+      float d[BATCH];
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        const int kk = min(k0 + j, nz - 1);
+        d[j] = __ldcs(pc + (size_t)kk * n2);  // streamed once: evict-first
+      }
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        const float dd = fabsf(d[j] - tp);
+        const int kk = k0 + j;
+        if (kk < nz && (kk == 0 || dd < best)) { best = dd; lev = kk; }
       }
     }
   } else {
-#pragma unroll
-    for (int q = 0; q < CPT; ++q) lev[q] = s_lev;
+    float diff = 1000000.0f;  // U:265-274
+    for (int k = 0; k < nz; ++k) {
+      const float dd = fabsf(__ldcs(pc + (size_t)k * n2) - tp);
+      if (dd <= diff) { lev = k; diff = dd; } else break;
+    }
   }
+  const float uu = __ldcs(a.u + (size_t)lev * n2 + c), vv = __ldcs(a.v + (size_t)lev * n2 + c);
+  float n_ws, n_wd;
+  wind_from_uv(a, uu, vv, n_ws, n_wd);
+  trigger_point<SBD_VARIANT_GENERIC>(a, (size_t)c, n2, a.thc[c], n_ws, n_wd, 0.0f);
+}
 
+// ------------------------------------------------------------------------------------------------
+// K4b', the vectorised form of k_scan_trigger: one thread per aligned QUAD of cells (linear
+// indices 4m..4m+3, at least one of them in the coastal zone), compacted in raster order.  Each
+// level of the four pressure columns arrives as one 16-byte load (LDG.128), BATCH of them in
+// flight per thread; the per-cell first-minimum search, wind, thresholds and state update are
+// exactly those of k_scan_trigger.  Needs nx*ny % 4 == 0 and 16-byte aligned p.
+// ------------------------------------------------------------------------------------------------
+// The columns are staged through shared memory with cp.async (LDGSTS): a thread issues G
+// 16-byte copies per group without holding registers for them, two groups are in flight per
+// thread (2*G*16 B = 448 B), and each thread only ever reads back its own slots, so the kernel
+// needs no block barrier at all.
+template <int G, int NT>
+__global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* __restrict__ quads,
+                                                  int n_quads)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_buf = reinterpret_cast<float4*>(smem_raw);  // [2][G][NT]
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * NT + tid;
+  if (i >= n_quads) return;
+  const int m = quads[i];
+  const int c0 = m * 4;
+  const size_t n2 = (size_t)a.g.nx * a.g.ny;
+  const size_t stride4 = n2 >> 2;
+  const float tp = a.prm.target_plev;
+  const int nz = a.nz;
+  const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
+  const int ngroups = (nz + G - 1) / G;
+
+  auto issue = [&](int g) {
+    float4* dst = s_buf + (size_t)((g & 1) * G) * NT + tid;
+    const int kbase = g * G;
 #pragma unroll
-  for (int q = 0; q < CPT; ++q) {
-    if (!inside[q]) continue;
-    const int gx = x0 + cx, gy = y0 + cy0 + q;
-    const size_t c = (size_t)gy * a.g.nx + gx;
-    uint8_t fl = 0;
-    if (VARIANT == SBD_VARIANT_GENERIC) {
-      if (!active[q]) {
-        a.sb[c] = a.prm.missing;  // G:176
-        if (a.flags) a.flags[c] = 0;
-        continue;
+    for (int j = 0; j < G; ++j) {
+      if (kbase + j < nz) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)j * NT);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa),
+                     "l"(pq + (size_t)(kbase + j) * stride4)
+                     : "memory");
       }
     }
-    float ws = 0.0f, wd = 0.0f, sb = a.prm.missing;
-    if (VARIANT == SBD_VARIANT_PYTHON) { ws = a.ws_in[c]; wd = a.wd_in[c]; }
-    float n_ws = 0.0f, n_wd = 0.0f;
-    if (active[q]) {
-      fl = 1;
-      const float uu = __ldg(a.u + (size_t)lev[q] * n2 + c), vv = __ldg(a.v + (size_t)lev[q] * n2 + c);
-      n_ws = sqrtf(uu * uu + vv * vv);                                   // G:225
-      n_wd = sbd_atan2f(-1.0f * uu, -1.0f * vv) * a.prm.rad2deg;         // G:227
-      if (VARIANT == SBD_VARIANT_GENERIC) {
-        if (a.first_step) { ws = n_ws; wd = n_wd; }                      // G:235-239
-        else { ws = a.ws[c]; wd = a.wd[c]; }
-      } else {
-        if (a.first_step) { ws = n_ws; wd = n_wd; }                      // P:236-240
-      }
-      const float thc_abs = fabsf(n_thc[q]);                             // G:242
-      const float mws = (ws + n_ws) / 2.0f;                              // G:243
-      const float dws = fabsf(ws - n_ws);                                // G:244
-      const float dwd = fabsf(sbd_modulo((wd - n_wd) + 180.0f, 360.0f) - 180.0f);  // G:246-247
-      if (dwd < a.prm.thresh_winddir && dws < a.prm.thresh_windch && mws < a.prm.thresh_wind &&
-          thc_abs > a.prm.thresh_thc) {                                  // G:249-252
-        const float scale_wind = (a.prm.thresh_wind - mws) / fmaxf(1.0f, mws);  // G:254
-        const float scale_thc = (thc_abs - a.prm.thresh_thc) / n_thc[q];        // G:255
-        sb = scale_thc * scale_wind;                                             // G:256
-        fl |= 2;
-      } else {
-        sb = 0.0f;                                                       // G:258
-      }
-    }
-    if (VARIANT == SBD_VARIANT_GENERIC) {
-      a.sb[c] = sb;
-      a.ws[c] = n_ws;                                                    // G:261
-      a.thc[c] = n_thc[q];                                               // G:262
-      if (a.six_hourly || a.first_step) a.wd[c] = n_wd;                  // G:237, G:264-266
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  issue(0);
+  // previous windspeed / winddir of the quad: stable since the last step, so they can be in
+  // flight together with the pressure columns (16-byte loads, the quad is aligned)
+  float4 ws4 = make_float4(0.f, 0.f, 0.f, 0.f), wd4 = ws4;
+  if (!a.first_step) {
+    ws4 = __ldcg(reinterpret_cast<const float4*>(a.ws) + m);
+    wd4 = __ldcg(reinterpret_cast<const float4*>(a.wd) + m);
+  }
+  float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+  int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    if (g + 1 < ngroups) {
+      issue(g + 1);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     } else {
-      if (active[q] && a.six_hourly) { ws = n_ws; wd = n_wd; }           // P:271-274
-      const int so = own_index<VARIANT>(a.g, gx, gy);
-      a.out[c] = sb;                                                     // P:277
-      a.out[n2 + c] = a.theta[so] - a.gzsm[so];                          // P:278
-      a.out[2 * n2 + c] = ws;                                            // P:279
-      a.out[3 * n2 + c] = wd;                                            // P:280
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
-    if (a.flags) a.flags[c] = fl;
+    const float4* src = s_buf + (size_t)((g & 1) * G) * NT + tid;
+    const int kbase = g * G;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int kk = kbase + j;
+      if (kk < nz) {
+        const float4 d = src[(size_t)j * NT];
+        const float e0 = fabsf(d.x - tp), e1 = fabsf(d.y - tp), e2 = fabsf(d.z - tp), e3 = fabsf(d.w - tp);
+        // minloc(abs(p - target_plev)): level 0 initialises, later levels need a strict < (G:223)
+        if (kk == 0 || e0 < b0) { b0 = e0; l0 = kk; }
+        if (kk == 0 || e1 < b1) { b1 = e1; l1 = kk; }
+        if (kk == 0 || e2 < b2) { b2 = e2; l2 = kk; }
+        if (kk == 0 || e3 < b3) { b3 = e3; l3 = kk; }
+      }
+    }
+  }
+  // which cells of the quad are in the coastal zone (static code plane, L2 resident)
+  bool act[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j;
+    const int y = c / a.g.nx, x = c - y * a.g.nx;
+    act[j] = (a.code[(size_t)(y + a.g.h) * a.g.ldx + (x + a.g.h)] & 0x7fffu) != 0;
+  }
+  // wind at the selected levels: all loads first
+  const int lv[4] = {l0, l1, l2, l3};
+  float uu[4], vv[4];
+  if (l0 == l1 && l1 == l2 && l2 == l3) {  // the usual case: one 16-byte load each
+    const float4 u4 = __ldcs(reinterpret_cast<const float4*>(a.u + (size_t)l0 * n2) + m);
+    const float4 v4 = __ldcs(reinterpret_cast<const float4*>(a.v + (size_t)l0 * n2) + m);
+    uu[0] = u4.x; uu[1] = u4.y; uu[2] = u4.z; uu[3] = u4.w;
+    vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uu[j] = __ldcs(a.u + (size_t)lv[j] * n2 + c0 + j);
+      vv[j] = __ldcs(a.v + (size_t)lv[j] * n2 + c0 + j);
+    }
+  }
+  float nws[4], nwd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wind_from_uv(a, uu[j], vv[j], nws[j], nwd[j]);
+  // n_thc comes from the window kernel, of which this grid is a programmatic dependent: it
+  // started while that kernel was still running and only now waits for it
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.thc) + m);
+  const float thc_[4] = {thc4.x, thc4.y, thc4.z, thc4.w};
+  const float wsp[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
+  const float wdp[4] = {wd4.x, wd4.y, wd4.z, wd4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (act[j]) {
+      const size_t c = (size_t)(c0 + j);
+      trigger_point_vals(a, c, thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
+    }
   }
 }
+
+// flag functor for the compaction of quads with at least one coastal-zone cell
+struct QuadFlag {
+  const uint16_t* code;
+  int nx, h, ldx;
+  __host__ __device__ __forceinline__ bool operator()(const int& m) const
+  {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = m * 4 + j;
+      const int y = c / nx, x = c - y * nx;
+      any |= (code[(size_t)(y + h) * ldx + (x + h)] & 0x7fffu) != 0;
+    }
+    return any;
+  }
+};
+
+// flag functor for the compaction of coastal-zone cells (interior, raster order)
+struct ActiveFlag {
+  const uint16_t* code;
+  int nx, h, ldx;
+  __host__ __device__ __forceinline__ bool operator()(const int& c) const
+  {
+    const int y = c / nx, x = c - y * nx;
+    return (code[(size_t)(y + h) * ldx + (x + h)] & 0x7fffu) != 0;
+  }
+};
 
 }  // namespace sbdk
 using namespace sbdk;
@@ -709,7 +1081,15 @@ struct sbd_plan {
   uint16_t* d_code = nullptr;
   float* d_stats = nullptr;   // 4 floats
   float* d_carry = nullptr;   // 5 floats
-  int* d_cnt = nullptr;       // nn_max, n_coastal
+  int* d_cnt = nullptr;       // nn_max, n_coastal, n_active (compaction)
+  int* d_idx = nullptr;       // compacted raster-ordered list of coastal-zone cells (dense index)
+  int* d_quads = nullptr;     // compacted list of aligned quads holding >= 1 coastal-zone cell
+  int n_quads = 0;
+  void* d_cub = nullptr;      // cub temp storage
+  size_t cub_bytes = 0;
+  // optional per-kernel CUDA-event timing of the step (bench.py roofline leg)
+  bool timing = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int nn_max = 0, n_coastal = 0;
   float stats[4] = {0, 0, 0, 0};
   bool have_static = false;
@@ -780,6 +1160,7 @@ int flush_out(sbd_plan* p, std::vector<OutView>& pend, bool any_host)
 int run_stats(cudaStream_t st, const float* d_ary, int nx, int ny, int ld, float* d_carry, float* d_stats)
 {
   const float fn = (float)(nx * ny);  // real(nlons*nlats)
+  CK(cudaMemsetAsync(d_carry, 0, 5 * sizeof(float), st));  // running sum starts at +0 (G:466)
   k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, 0, 1, d_carry); LAUNCHED();
   k_stats_finish<<<1, 1, 0, st>>>(d_carry, fn, 0, d_stats); LAUNCHED();
   k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, 1, 0, d_carry); LAUNCHED();
@@ -832,12 +1213,71 @@ template <int VARIANT>
 int launch_trigger(sbd_plan* p, TrigArgs& a)
 {
   constexpr int TX = 64, TY = 16, NT = 256;
+  constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
   const int R = a.R;
-  const size_t smem = (size_t)(TX + 2 * R) * (TY + 2 * R) * 5;
-  auto kern = k_trigger<VARIANT, TX, TY, NT>;
+  const size_t cells = (size_t)(TX + 2 * R) * (TY + 2 * R);
+  const size_t smem = cells * 4 + ((size_t)(TY + 2 * R) * ((TX + 2 * R + 31) / 32) + 2) * 4 + (size_t)TX * TY * 4;
+  auto kern = k_trigger<VARIANT, TX, TY, NT, GEN>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+  if (!GEN) {
+    if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+    kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();
+    if (p->timing) { CK(cudaEventRecord(p->ev[1], p->stream)); }
+    CK(cudaGetLastError());
+    return SBD_OK;
+  }
+  const bool vec = p->n_quads > 0 && a.prm.level_scan == 0 && (((uintptr_t)a.p) & 15) == 0;
+  if (!vec) {
+    // scalar path (nx*ny not a multiple of 4, unaligned p, or the UM early-exit scan): in order
+    if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+    kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();
+    if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+    if (p->n_coastal > 0) {
+      k_scan_trigger<14><<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
+    }
+    if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
+    CK(cudaGetLastError());
+    return SBD_OK;
+  }
+  // window kernel, then the level-scan kernel as its programmatic dependent: the scan's CTAs
+  // start streaming p as soon as SM resources allow (the window kernel signals
+  // launch_dependents on entry) and only wait for n_thc in their epilogue.
+  constexpr int QNT = 128;
+  static int G = 0;
+  if (!G) {
+    const char* e = getenv("SBD_SCAN_G");
+    G = e ? atoi(e) : 10;
+    if (G != 5 && G != 7 && G != 10 && G != 14) G = 10;
+    CK(cudaFuncSetAttribute(k_scan_quad<5, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 5 * QNT * 16));
+    CK(cudaFuncSetAttribute(k_scan_quad<7, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 7 * QNT * 16));
+    CK(cudaFuncSetAttribute(k_scan_quad<10, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 10 * QNT * 16));
+    CK(cudaFuncSetAttribute(k_scan_quad<14, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 14 * QNT * 16));
+  }
+  const int qsmem = 2 * G * QNT * 16;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
   kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();
+  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cdiv(p->n_quads, QNT));
+    cfg.blockDim = dim3(QNT);
+    cfg.dynamicSmemBytes = qsmem;
+    cfg.stream = p->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = p->timing ? 0 : 1;  // timed runs: kernels in isolation
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int* quads = p->d_quads;
+    int nq = p->n_quads;
+    if (G == 5) CK(cudaLaunchKernelEx(&cfg, k_scan_quad<5, QNT>, (const TrigArgs)a, quads, nq));
+    else if (G == 7) CK(cudaLaunchKernelEx(&cfg, k_scan_quad<7, QNT>, (const TrigArgs)a, quads, nq));
+    else if (G == 10) CK(cudaLaunchKernelEx(&cfg, k_scan_quad<10, QNT>, (const TrigArgs)a, quads, nq));
+    else CK(cudaLaunchKernelEx(&cfg, k_scan_quad<14, QNT>, (const TrigArgs)a, quads, nq));
+    LAUNCHED();
+  }
+  if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
   CK(cudaGetLastError());
   return SBD_OK;
 }
@@ -932,6 +1372,12 @@ int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, 
   if ((long long)(nx + 2 * h) * (ny + 2 * h) > 0x7fffffffLL) return fail(SBD_EDIMS, "plane too large for 32-bit indexing");
   int rc = ensure_device();
   if (rc) return rc;
+  if (const char* gr = getenv("SBD_L2_FETCH_GRANULARITY")) {
+    // experiment knob: the p-column gather touches short runs of cells; a 32 B fetch granule
+    // wastes less DRAM traffic than the default 64 B
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));
+    cudaGetLastError();
+  }
   sbd_plan* p = new sbd_plan();
   p->variant = variant; p->nx = nx; p->ny = ny; p->nz = nz;
   p->h = (variant == SBD_VARIANT_GENERIC) ? h : 0;
@@ -945,7 +1391,9 @@ int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, 
       cudaMalloc((void**)&p->d_code, n * sizeof(uint16_t)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_stats, 4 * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_carry, 5 * sizeof(float)) != cudaSuccess ||
-      cudaMalloc((void**)&p->d_cnt, 2 * sizeof(int)) != cudaSuccess) {
+      cudaMalloc((void**)&p->d_cnt, 4 * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_idx, (size_t)nx * ny * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_quads, ((size_t)nx * ny / 4 + 1) * sizeof(int)) != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "cudaMalloc of plan planes failed: %s", cudaGetErrorString(cudaGetLastError()));
     sbd_plan_destroy(p);
     return SBD_ECUDA;
@@ -959,6 +1407,8 @@ void sbd_plan_destroy(sbd_plan* p)
   if (!p) return;
   if (p->own_stream) cudaStreamSynchronize(p->own_stream);
   cudaFree(p->d_gzsm); cudaFree(p->d_code); cudaFree(p->d_stats); cudaFree(p->d_carry); cudaFree(p->d_cnt);
+  cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads);
+  for (int i = 0; i < 6; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   for (auto& s : p->stage) cudaFree(s.first);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
@@ -967,7 +1417,30 @@ void sbd_plan_destroy(sbd_plan* p)
 int sbd_plan_set_stream(sbd_plan* p, void* stream)
 {
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
-  p->stream = stream ? (cudaStream_t)stream : p->own_stream;
+  p->stream = (cudaStream_t)stream;  // NULL = the legacy default stream (torch's default stream)
+  return SBD_OK;
+}
+int sbd_plan_set_timing(sbd_plan* p, int on)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  if (on && !p->ev[0])
+    for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&p->ev[i]));
+  p->timing = on != 0;
+  return SBD_OK;
+}
+int sbd_plan_last_timing(sbd_plan* p, float* ms3)
+{
+  if (!p || !ms3 || !p->ev[0]) return fail(SBD_EINVAL, "timing was not enabled");
+  ms3[0] = ms3[1] = ms3[2] = 0.0f;
+  CK(cudaStreamSynchronize(p->stream));
+  CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));  // window kernel
+  if (p->variant == SBD_VARIANT_GENERIC) CK(cudaEventElapsedTime(&ms3[1], p->ev[1], p->ev[2]));  // scan kernel
+  return SBD_OK;
+}
+int sbd_plan_use_own_stream(sbd_plan* p)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  p->stream = p->own_stream;
   return SBD_OK;
 }
 void* sbd_plan_get_stream(sbd_plan* p) { return p ? (void*)p->stream : nullptr; }
@@ -1012,12 +1485,45 @@ int sbd_plan_set_static(sbd_plan* p, const float* mask, const float* z, const fl
   }
   LAUNCHED();
   CK(cudaGetLastError());
-  int cnt[2];
+  {
+    // compacted list of coastal-zone cells, raster order (static)
+    const int n2 = p->nx * p->ny;
+    cub::CountingInputIterator<int> it(0);
+    ActiveFlag fl{p->d_code, p->nx, p->h, p->g.ldx};
+    size_t need = 0;
+    CK(cub::DeviceSelect::If(nullptr, need, it, p->d_idx, p->d_cnt + 2, n2, fl, st));
+    if (need > p->cub_bytes) {
+      CK(cudaFree(p->d_cub));
+      p->d_cub = nullptr;
+      CK(cudaMalloc(&p->d_cub, need));
+      p->cub_bytes = need;
+    }
+    CK(cub::DeviceSelect::If(p->d_cub, need, it, p->d_idx, p->d_cnt + 2, n2, fl, st));
+    LAUNCHED();
+    CK(cudaMemsetAsync(p->d_cnt + 3, 0, sizeof(int), st));
+    if (n2 % 4 == 0 && p->variant == SBD_VARIANT_GENERIC) {
+      QuadFlag qf{p->d_code, p->nx, p->h, p->g.ldx};
+      size_t need2 = 0;
+      CK(cub::DeviceSelect::If(nullptr, need2, it, p->d_quads, p->d_cnt + 3, n2 / 4, qf, st));
+      if (need2 > p->cub_bytes) {
+        CK(cudaStreamSynchronize(st));
+        CK(cudaFree(p->d_cub));
+        p->d_cub = nullptr;
+        CK(cudaMalloc(&p->d_cub, need2));
+        p->cub_bytes = need2;
+      }
+      CK(cub::DeviceSelect::If(p->d_cub, need2, it, p->d_quads, p->d_cnt + 3, n2 / 4, qf, st));
+      LAUNCHED();
+    }
+  }
+  int cnt[4];
   CK(cudaMemcpyAsync(cnt, p->d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(p->stats, p->d_stats, sizeof p->stats, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   p->nn_max = cnt[0];
   p->n_coastal = cnt[1];
+  p->n_quads = cnt[3];
+  if (cnt[2] != cnt[1]) return fail(SBD_ECUDA, "internal: compaction count differs from the coastal-cell count");
   p->R = min(p->nn_max, 16);
   p->have_static = true;
   return SBD_OK;
@@ -1189,6 +1695,16 @@ int sbd_swap_bounds_ew_f32(float* field, int nx, int ny, int h)
   if ((rc = t.out(field, (size_t)(nx + 2 * h) * (ny + 2 * h) * 4, true, &d))) return rc;
   if ((rc = swap_bounds_dev(t.st, (float*)d, nx, ny, h, false))) return rc;
   return t.finish();
+}
+
+int sbd_swap_bounds_dev_f32(float* d_field, int nx, int ny, int h, int ns_mask, void* stream)
+{
+  if (!d_field || nx < 1 || ny < 1 || h < 0) return fail(SBD_EINVAL, "bad argument");
+  if (h == 0) return SBD_OK;
+  const long long n = 2LL * h * (nx + 2 * h) + 2LL * h * ny;
+  k_halo_all<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_field, nx, ny, h, ns_mask); LAUNCHED();
+  CK(cudaGetLastError());
+  return SBD_OK;
 }
 
 int sbd_py_get_edges_f32(const float* lsm, const float* ci, int nlons, int nlats, float* coast)

@@ -133,6 +133,18 @@ class Plan:
     def stream(self):
         return self.lib.sbd_plan_get_stream(self._h)
 
+    def use_own_stream(self):
+        _capi.check(self.lib.sbd_plan_use_own_stream(self._h), "plan_use_own_stream")
+
+    def set_timing(self, on):
+        _capi.check(self.lib.sbd_plan_set_timing(self._h, 1 if on else 0), "plan_set_timing")
+
+    def last_timing(self):
+        """(window kernel, scan kernel, join+final kernel) ms of the last step; needs set_timing(True)."""
+        ms = np.zeros(3, dtype=np.float32)
+        _capi.check(self.lib.sbd_plan_last_timing(self._h, _capi.ptr(ms)), "plan_last_timing")
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
     def sync(self):
         _capi.check(self.lib.sbd_plan_sync(self._h), "plan_sync")
 

@@ -1,0 +1,94 @@
+"""swap_bounds across GPUs: the reference's halo_exchange_mod::swap_bounds (generic/
+halo_exchange_mod.f90:12-17 is an empty stub; the UM's real one is MPI, UM/vn10.7/
+sea_breeze_diag.F90:408-410) as NCCL send/recv between latitude row blocks.
+
+Decomposition: 1-D row blocks along latitude, one process per GPU.  A halo'd
+block is (ny_loc + 2h, nx + 2h); halo rows are contiguous, so each exchange is two sends and two
+receives of h*(nx+2h) floats.  East-west periodic wrap stays on the GPU (one kernel,
+sbd_swap_bounds_dev_f32); domain edges (first/last rank) replicate the edge row.
+
+The sigmoid statistics (generic/sea_breeze_diag.f90:466-478) are sequential fp32 accumulations over
+the *global* grid in memory order; with row blocks every rank's chunk is contiguous in that
+order, so the chain is a rank-ordered pipeline of carries (global_sigma_stats), done once per
+plan.
+"""
+import numpy as np
+
+from . import _capi
+
+
+class RowBlockHalo:
+    def __init__(self, nx, ny_local, h, rank=0, world=1, device=None, group=None):
+        self.nx, self.ny, self.h = nx, ny_local, h
+        self.rank, self.world = rank, world
+        self.device = device
+        self.group = group
+        self.lib = _capi.load()
+        self.up = rank - 1 if rank > 0 else None       # owns the rows above (smaller latitude index)
+        self.down = rank + 1 if rank < world - 1 else None
+        self.ns_mask = (1 if self.up is None else 0) | (2 if self.down is None else 0)
+        self.launches_per_step = 1
+
+    # -- halo fill of one halo'd field (torch CUDA tensor, (ny+2h, nx+2h), contiguous float32) --
+    def swap_bounds(self, field):
+        import torch
+        h, ny = self.h, self.ny
+        stream = torch.cuda.current_stream(field.device).cuda_stream
+        _capi.check(self.lib.sbd_swap_bounds_dev_f32(field.data_ptr(), self.nx, ny, h, self.ns_mask, stream),
+                    "swap_bounds")
+        if self.world > 1:
+            import torch.distributed as dist
+            ops = []
+            if self.up is not None:
+                ops.append(dist.P2POp(dist.isend, field[h:2 * h], self.up, self.group))
+                ops.append(dist.P2POp(dist.irecv, field[0:h], self.up, self.group))
+            if self.down is not None:
+                ops.append(dist.P2POp(dist.isend, field[ny:ny + h], self.down, self.group))
+                ops.append(dist.P2POp(dist.irecv, field[ny + h:ny + 2 * h], self.down, self.group))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return field
+
+    swap_bounds_step = swap_bounds
+
+    # -- global sequential statistics of sigma over all ranks' interiors (rank-ordered carry) --
+    def global_sigma_stats(self, sigma_h):
+        """Returns float32[3] = mean, 2/sqrt(var/n), (max-min)/4 of the global interior, evaluated in
+        the reference's sequential order (rank-major == global memory order)."""
+        import torch
+        import torch.distributed as dist
+        h, ny, nx = self.h, self.ny, self.nx
+        ldx = nx + 2 * h
+        interior = sigma_h.data_ptr() + 4 * (h * ldx + h)
+        dev = sigma_h.device
+        carry = np.zeros(5, dtype=np.float32)
+        n_glob = np.float32(nx * ny * self.world)
+
+        def chain(pass_no):
+            nonlocal carry
+            buf = torch.zeros(5, dtype=torch.float32, device=dev)
+            if self.up is not None:
+                dist.recv(buf, self.up, group=self.group)
+                carry = buf.cpu().numpy().copy()
+            first = 1 if (self.up is None and pass_no == 0) else 0
+            _capi.check(self.lib.sbd_stats_chain_f32(interior, nx, ny, ldx, pass_no, first, carry.ctypes.data),
+                        "stats_chain")
+            if self.down is not None:
+                dist.send(torch.from_numpy(carry).to(dev), self.down, group=self.group)
+            # the last rank holds the global carry: broadcast it
+            out = torch.from_numpy(carry).to(dev)
+            dist.broadcast(out, self.world - 1, group=self.group)
+            return out.cpu().numpy().copy()
+
+        c0 = chain(0)
+        mean = np.float32(c0[0] / n_glob)
+        carry = c0.copy()
+        carry[1] = np.float32(0.0)
+        carry[4] = mean
+        if self.up is not None:
+            pass  # carry is overwritten by the received one in chain(1)
+        c1 = chain(1)
+        var = np.float32(c1[1])
+        std = np.float32(np.float32(2.0) / np.sqrt(np.float32(var / n_glob)))
+        r = np.float32(np.float32(c0[2] - c0[3]) / np.float32(4.0))
+        return np.array([mean, std, r], dtype=np.float32)

@@ -1125,10 +1125,31 @@ int stage_get(sbd_plan* p, size_t bytes, void** out)
   return SBD_OK;
 }
 
+// Pinned (page-locked, device-mapped) host memory can be read by the kernels in place over PCIe.
+// The level scan touches only the pressure columns of coastal-zone cells and one level of u,v,
+// so for these large 3-D arrays a zero-copy gather moves a fraction of the bytes a staged copy
+// would.  SBD_ZERO_COPY=0 disables it.
+const float* mapped_host_ptr(const float* src)
+{
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SBD_ZERO_COPY");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, src) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type == cudaMemoryTypeHost && at.devicePointer) return (const float*)at.devicePointer;
+  return nullptr;
+}
+
 // device view of an input array
-int in_view(sbd_plan* p, const float* src, size_t n, const float** out)
+int in_view(sbd_plan* p, const float* src, size_t n, const float** out, bool zero_copy_ok = false)
 {
   if (is_device_ptr(src)) { *out = src; return SBD_OK; }
+  if (zero_copy_ok) {
+    if (const float* m = mapped_host_ptr(src)) { *out = m; return SBD_OK; }
+  }
   void* d;
   int rc = stage_get(p, n * sizeof(float), &d);
   if (rc) return rc;
@@ -1555,9 +1576,9 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
   TrigArgs a{};
   int rc;
   const bool any_host = !is_device_ptr(pp) || !is_device_ptr(theta) || !is_device_ptr(u) || !is_device_ptr(v);
-  if ((rc = in_view(p, pp, n3, &a.p))) return rc;
-  if ((rc = in_view(p, u, n3, &a.u))) return rc;
-  if ((rc = in_view(p, v, n3, &a.v))) return rc;
+  if ((rc = in_view(p, pp, n3, &a.p, true))) return rc;
+  if ((rc = in_view(p, u, n3, &a.u, true))) return rc;
+  if ((rc = in_view(p, v, n3, &a.v, true))) return rc;
   if ((rc = in_view(p, theta, nh, &a.theta))) return rc;
   const bool first = step < 2;
   void* d;
@@ -1589,9 +1610,10 @@ int sbd_plan_step_py(sbd_plan* p, int step, float timestep_min, const float* pp,
   const bool any_host = !is_device_ptr(pp) || !is_device_ptr(theta) || !is_device_ptr(u) ||
                         !is_device_ptr(v) || !is_device_ptr(ws) || !is_device_ptr(wd);
   if ((rc = in_view(p, pp, p->nz, &a.p))) return rc;
-  // only the selected level of u,v is read, but the level is chosen on the device: stage all
-  if ((rc = in_view(p, u, n3, &a.u))) return rc;
-  if ((rc = in_view(p, v, n3, &a.v))) return rc;
+  // only the selected level of u,v is read, and the level is chosen on the device: pinned host
+  // arrays are gathered in place, pageable ones are staged whole
+  if ((rc = in_view(p, u, n3, &a.u, true))) return rc;
+  if ((rc = in_view(p, v, n3, &a.v, true))) return rc;
   if ((rc = in_view(p, theta, n2, &a.theta))) return rc;
   if ((rc = in_view(p, ws, n2, &a.ws_in))) return rc;
   if ((rc = in_view(p, wd, n2, &a.wd_in))) return rc;

@@ -167,6 +167,12 @@ int sbd_plan_info(sbd_plan* plan, int* nn_max, int* n_coastal, float* stats4);
 int sbd_plan_step(sbd_plan* plan, float timestep, int timestep_number, const float* p, const float* u,
                   const float* v, const float* theta, float* windspeed, float* winddir, float* thc,
                   float* sb_con, uint8_t* flags);
+/* The same step in two calls, for callers that have something to do in between (multi-GPU: the
+ * halo exchange of theta runs while the level scan streams p).  sbd_plan_step_scan needs p,u,v
+ * only; sbd_plan_step_finish needs theta (with valid halos) and the state arrays. */
+int sbd_plan_step_scan(sbd_plan* plan, const float* p, const float* u, const float* v);
+int sbd_plan_step_finish(sbd_plan* plan, float timestep, int timestep_number, const float* theta,
+                         float* windspeed, float* winddir, float* thc, float* sb_con, uint8_t* flags);
 /* One time record, python variant (P:160-284).  timestep in minutes as in P. */
 int sbd_plan_step_py(sbd_plan* plan, int timestep_number, float timestep_min, const float* p,
                      const float* u, const float* v, const float* theta, const float* windspeed,
@@ -174,8 +180,8 @@ int sbd_plan_step_py(sbd_plan* plan, int timestep_number, float timestep_min, co
 /* Per-kernel CUDA-event timing of the step (off by default), events recorded on the stream the
  * kernels are launched on.  While timing is on the two kernels of the generic step run strictly
  * one after the other (no programmatic dependent launch), so each duration is that kernel alone:
- * ms3[0] = window / thermal-contrast kernel (k_trigger), ms3[1] = level-scan + trigger kernel
- * (k_scan_quad), ms3[2] = 0 (reserved).  Python variant: one kernel, ms3[1] = 0. */
+ * ms3[0] = window + threshold kernel (k_trigger), ms3[1] = level-scan kernel (k_scan_quad),
+ * ms3[2] = 0 (reserved).  Python variant: one kernel, ms3[1] = 0. */
 int sbd_plan_set_timing(sbd_plan* plan, int on);
 int sbd_plan_last_timing(sbd_plan* plan, float* ms3);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */

@@ -43,6 +43,25 @@ def build(force=False, verbose=False):
     return OUT
 
 
+HARNESS_SRC = os.path.join(HERE, "csrc", "dummy_model_harness.cpp")
+HARNESS = os.path.join(OUT_DIR, "dummy_model_harness")
+
+
+def build_harness(force=False):
+    """g++ build of the dummy_model call-sequence harness against the C-ABI library."""
+    build(force=False)
+    if not force and os.path.exists(HARNESS) and os.path.getmtime(HARNESS) >= max(
+            os.path.getmtime(HARNESS_SRC), os.path.getmtime(OUT)):
+        return HARNESS
+    cmd = ["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), HARNESS_SRC, "-o", HARNESS,
+           "-L" + OUT_DIR, "-lsbd_b200", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("harness build failed:\n" + res.stdout + res.stderr)
+    return HARNESS
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_harness(force="--force" in sys.argv))

@@ -537,6 +537,9 @@ struct TrigArgs {
   // python: inputs ws_in, wd_in; output (nx,ny,4)
   const float* ws_in; const float* wd_in; float* out;
   uint8_t* flags;
+  // generic: wind speed / direction at the selected level, written by the level-scan kernel and
+  // consumed by the window kernel's threshold stage (plan-owned scratch planes, nx x ny)
+  float* nws; float* nwd;
 };
 
 template <int VARIANT>
@@ -594,31 +597,6 @@ __device__ __forceinline__ void trigger_point(const TrigArgs& a, size_t c, size_
     a.out[2 * n2 + c] = ws;                                               // P:279
     a.out[3 * n2 + c] = wd;                                               // P:280
   }
-  if (a.flags) a.flags[c] = fl;
-}
-
-// generic-variant thresholds with the previous windspeed / winddir already in registers
-__device__ __forceinline__ void trigger_point_vals(const TrigArgs& a, size_t c, float n_thc, float n_ws,
-                                                   float n_wd, float ws_prev, float wd_prev)
-{
-  float ws = ws_prev, wd = wd_prev;
-  if (a.first_step) { ws = n_ws; wd = n_wd; }                             // G:235-239
-  const float thc_abs = fabsf(n_thc);                                     // G:242
-  const float mws = (ws + n_ws) / 2.0f;                                   // G:243
-  const float dws = fabsf(ws - n_ws);                                     // G:244
-  const float dwd = fabsf(sbd_modulo((wd - n_wd) + 180.0f, 360.0f) - 180.0f);  // G:246-247
-  float sb = 0.0f;                                                        // G:258
-  uint8_t fl = 1;
-  if (dwd < a.prm.thresh_winddir && dws < a.prm.thresh_windch && mws < a.prm.thresh_wind &&
-      thc_abs > a.prm.thresh_thc) {                                       // G:249-252
-    const float scale_wind = (a.prm.thresh_wind - mws) / fmaxf(1.0f, mws);  // G:254
-    const float scale_thc = (thc_abs - a.prm.thresh_thc) / n_thc;           // G:255
-    sb = scale_thc * scale_wind;                                             // G:256
-    fl = 3;
-  }
-  a.sb[c] = sb;
-  a.ws[c] = n_ws;                                                         // G:261
-  if (a.six_hourly || a.first_step) a.wd[c] = n_wd;                       // G:237, G:264-266
   if (a.flags) a.flags[c] = fl;
 }
 
@@ -681,10 +659,6 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
 
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int tid = threadIdx.x;
-
-  // programmatic dependent launch: let the level-scan kernel that follows in the stream start
-  // right away; it waits (griddepcontrol.wait) only before it consumes n_thc
-  if (SPLIT) asm volatile("griddepcontrol.launch_dependents;");
 
   if (tid < NB) s_cnt[tid] = 0;
   // ---- python: one pressure level for the whole grid (P:228), first minimum of |p - target| ----
@@ -780,6 +754,7 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
   n_list = s_off[NB - 1] + s_cnt[NB - 1];
 
   // ---- phase 3 ----
+  bool waited = false;
   for (int e = tid; e < n_list; e += NT) {
     const uint32_t ent = s_list[e];
     const int lid = (int)(ent & 0xffffu);
@@ -837,7 +812,12 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
     const float n_thc = mul * ((T_l / n_l) - (T_s / n_s));      // G:216
     const size_t c = (size_t)gy * a.g.nx + gx;
     if (SPLIT) {
+      // generic: the level scan (k_scan_quad / k_scan_scalar) is the kernel launched just before
+      // this one; this grid is its programmatic dependent, so everything up to here overlapped
+      // with it.  Wait for its n_ws / n_wd, then thresholds + state update (G:235-266).
+      if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
       a.thc[c] = n_thc;                                         // G:262
+      trigger_point<VARIANT>(a, c, n2, n_thc, __ldcg(a.nws + c), __ldcg(a.nwd + c), 0.0f);
     } else if (VARIANT == SBD_VARIANT_PYTHON) {
       const int lev = s_lev;
       const float uu = __ldg(a.u + (size_t)lev * n2 + c), vv = __ldg(a.v + (size_t)lev * n2 + c);
@@ -871,16 +851,17 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4b scan+trigger (generic variant): one thread per coastal-zone cell of the compacted, raster-
-// ordered list idx[].  Streams the cell's pressure column (nz levels, stride nx*ny) with BATCH
-// independent loads in flight per thread, finds the first minimum of |p - target_plev| (G:223),
-// then wind, thresholds, scaling and state update (G:225-266).  n_thc was written to thc[] by
-// k_trigger<SPLIT>.
+// K4b level scan, scalar form (generic variant; used when nx*ny is not a multiple of 4, p is not
+// 16-byte aligned, or for the UM early-exit scan): one thread per coastal-zone cell of the
+// compacted, raster-ordered list idx[].  Streams the cell's pressure column (nz levels, stride
+// nx*ny), finds the level (G:223 / U:265-274) and leaves the wind speed / direction at that level
+// (G:225-227) in the scratch planes for the window kernel's threshold stage.
 // ------------------------------------------------------------------------------------------------
 template <int BATCH>
-__global__ void __launch_bounds__(256) k_scan_trigger(const TrigArgs a, const int* __restrict__ idx,
-                                                      int n_active)
+__global__ void __launch_bounds__(256) k_scan_scalar(const TrigArgs a, const int* __restrict__ idx,
+                                                     int n_active)
 {
+  asm volatile("griddepcontrol.launch_dependents;");
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_active) return;
   const int c = idx[i];
@@ -890,7 +871,7 @@ __global__ void __launch_bounds__(256) k_scan_trigger(const TrigArgs a, const in
   const int nz = a.nz;
   int lev = 0;
   if (a.prm.level_scan == 0) {
-    float best = __int_as_float(0x7f800000);
+    float best = 0.0f;
     for (int k0 = 0; k0 < nz; k0 += BATCH) {
       float d[BATCH];
 #pragma unroll
@@ -902,7 +883,7 @@ __global__ void __launch_bounds__(256) k_scan_trigger(const TrigArgs a, const in
       for (int j = 0; j < BATCH; ++j) {
         const float dd = fabsf(d[j] - tp);
         const int kk = k0 + j;
-        if (kk < nz && (kk == 0 || dd < best)) { best = dd; lev = kk; }
+        if (kk < nz && (kk == 0 || dd < best)) { best = dd; lev = kk; }  // minloc, first minimum (G:223)
       }
     }
   } else {
@@ -915,15 +896,16 @@ __global__ void __launch_bounds__(256) k_scan_trigger(const TrigArgs a, const in
   const float uu = __ldcs(a.u + (size_t)lev * n2 + c), vv = __ldcs(a.v + (size_t)lev * n2 + c);
   float n_ws, n_wd;
   wind_from_uv(a, uu, vv, n_ws, n_wd);
-  trigger_point<SBD_VARIANT_GENERIC>(a, (size_t)c, n2, a.thc[c], n_ws, n_wd, 0.0f);
+  a.nws[c] = n_ws;
+  a.nwd[c] = n_wd;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4b', the vectorised form of k_scan_trigger: one thread per aligned QUAD of cells (linear
+// K4b', the vectorised form of k_scan_scalar: one thread per aligned QUAD of cells (linear
 // indices 4m..4m+3, at least one of them in the coastal zone), compacted in raster order.  Each
-// level of the four pressure columns arrives as one 16-byte load (LDG.128), BATCH of them in
-// flight per thread; the per-cell first-minimum search, wind, thresholds and state update are
-// exactly those of k_scan_trigger.  Needs nx*ny % 4 == 0 and 16-byte aligned p.
+// level of the four pressure columns arrives as one 16-byte copy; the per-cell first-minimum
+// search and the wind at the selected level are exactly those of k_scan_scalar.
+// Needs nx*ny % 4 == 0 and 16-byte aligned p.
 // ------------------------------------------------------------------------------------------------
 // The columns are staged through shared memory with cp.async (LDGSTS): a thread issues G
 // 16-byte copies per group without holding registers for them, two groups are in flight per
@@ -947,6 +929,10 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
   const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
   const int ngroups = (nz + G - 1) / G;
 
+  // p is streamed exactly once: mark its lines evict-first in L2 so that the small planes the
+  // window kernel re-reads every step (gzsm, code, state, scratch) stay resident beside the stream
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   auto issue = [&](int g) {
     float4* dst = s_buf + (size_t)((g & 1) * G) * NT + tid;
     const int kbase = g * G;
@@ -954,8 +940,8 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
     for (int j = 0; j < G; ++j) {
       if (kbase + j < nz) {
         const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)j * NT);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa),
-                     "l"(pq + (size_t)(kbase + j) * stride4)
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa),
+                     "l"(pq + (size_t)(kbase + j) * stride4), "l"(pol)
                      : "memory");
       }
     }
@@ -963,13 +949,9 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
   };
 
   issue(0);
-  // previous windspeed / winddir of the quad: stable since the last step, so they can be in
-  // flight together with the pressure columns (16-byte loads, the quad is aligned)
-  float4 ws4 = make_float4(0.f, 0.f, 0.f, 0.f), wd4 = ws4;
-  if (!a.first_step) {
-    ws4 = __ldcg(reinterpret_cast<const float4*>(a.ws) + m);
-    wd4 = __ldcg(reinterpret_cast<const float4*>(a.wd) + m);
-  }
+  // the window kernel launched next in the stream may start now (programmatic dependent launch);
+  // it waits for this grid only before it reads n_ws / n_wd
+  asm volatile("griddepcontrol.launch_dependents;");
   float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
   int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
   for (int g = 0; g < ngroups; ++g) {
@@ -1021,19 +1003,13 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
   float nws[4], nwd[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) wind_from_uv(a, uu[j], vv[j], nws[j], nwd[j]);
-  // n_thc comes from the window kernel, of which this grid is a programmatic dependent: it
-  // started while that kernel was still running and only now waits for it
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.thc) + m);
-  const float thc_[4] = {thc4.x, thc4.y, thc4.z, thc4.w};
-  const float wsp[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
-  const float wdp[4] = {wd4.x, wd4.y, wd4.z, wd4.w};
+  if (act[0] && act[1] && act[2] && act[3]) {
+    reinterpret_cast<float4*>(a.nws)[m] = make_float4(nws[0], nws[1], nws[2], nws[3]);
+    reinterpret_cast<float4*>(a.nwd)[m] = make_float4(nwd[0], nwd[1], nwd[2], nwd[3]);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (act[j]) {
-      const size_t c = (size_t)(c0 + j);
-      trigger_point_vals(a, c, thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
-    }
+    for (int j = 0; j < 4; ++j)
+      if (act[j]) { a.nws[c0 + j] = nws[j]; a.nwd[c0 + j] = nwd[j]; }
   }
 }
 
@@ -1087,6 +1063,10 @@ struct sbd_plan {
   int n_quads = 0;
   void* d_cub = nullptr;      // cub temp storage
   size_t cub_bytes = 0;
+  float* d_nws = nullptr;     // scratch: wind speed at the selected level (scan -> window kernel)
+  float* d_nwd = nullptr;     // scratch: wind direction at the selected level
+  bool scan_done = false;     // sbd_plan_step_scan has been issued for the current step
+  const float *cur_p = nullptr, *cur_u = nullptr, *cur_v = nullptr;
   // optional per-kernel CUDA-event timing of the step (bench.py roofline leg)
   bool timing = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1230,6 +1210,62 @@ int dist_dev(cudaStream_t st, const float* d_coast, int coast_ld, int coast_off,
   return SBD_OK;
 }
 
+// generic step, stage 1: level scan over p (+ wind at the selected level) into the scratch planes.
+// Needs p,u,v only -- neither theta nor its halos -- so a multi-GPU caller runs its halo exchange
+// beside it.
+int launch_scan(sbd_plan* p, TrigArgs& a)
+{
+  a.nws = p->d_nws;
+  a.nwd = p->d_nwd;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+  if (p->n_coastal > 0) {
+    const bool vec = p->n_quads > 0 && a.prm.level_scan == 0 && (((uintptr_t)a.p) & 15) == 0 &&
+                     (((uintptr_t)a.u) & 15) == 0 && (((uintptr_t)a.v) & 15) == 0;
+    if (vec) {
+      constexpr int QNT = 128;
+      static int G = 0;
+      if (!G) {
+        const char* e = getenv("SBD_SCAN_G");
+        G = e ? atoi(e) : 10;
+        if (G != 5 && G != 7 && G != 10 && G != 14) G = 10;
+        CK(cudaFuncSetAttribute(k_scan_quad<5, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 5 * QNT * 16));
+        CK(cudaFuncSetAttribute(k_scan_quad<7, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 7 * QNT * 16));
+        CK(cudaFuncSetAttribute(k_scan_quad<10, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 10 * QNT * 16));
+        CK(cudaFuncSetAttribute(k_scan_quad<14, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 14 * QNT * 16));
+      }
+      // Shared memory per scan CTA also sets how many of them an SM holds, i.e. how much room is
+      // left for the window kernel's CTAs that run beside them (programmatic dependent launch).
+      static int pad_kb = -1;
+      if (pad_kb < 0) { const char* e = getenv("SBD_SCAN_SMEM_KB"); pad_kb = e ? atoi(e) : 0; }
+      int qsmem = 2 * G * QNT * 16;
+      if (pad_kb * 1024 > qsmem) {
+        qsmem = pad_kb * 1024;
+        static bool once = false;
+        if (!once) {
+          once = true;
+          CK(cudaFuncSetAttribute(k_scan_quad<5, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
+          CK(cudaFuncSetAttribute(k_scan_quad<7, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
+          CK(cudaFuncSetAttribute(k_scan_quad<10, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
+          CK(cudaFuncSetAttribute(k_scan_quad<14, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
+        }
+      }
+      const int nb = cdiv(p->n_quads, QNT);
+      if (G == 5) k_scan_quad<5, QNT><<<nb, QNT, qsmem, p->stream>>>(a, p->d_quads, p->n_quads);
+      else if (G == 7) k_scan_quad<7, QNT><<<nb, QNT, qsmem, p->stream>>>(a, p->d_quads, p->n_quads);
+      else if (G == 10) k_scan_quad<10, QNT><<<nb, QNT, qsmem, p->stream>>>(a, p->d_quads, p->n_quads);
+      else k_scan_quad<14, QNT><<<nb, QNT, qsmem, p->stream>>>(a, p->d_quads, p->n_quads);
+      LAUNCHED();
+    } else {
+      k_scan_scalar<14><<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
+    }
+  }
+  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+
+// window kernel (+ thresholds).  Generic: launched as the programmatic dependent of the scan kernel
+// that precedes it in the stream.
 template <int VARIANT>
 int launch_trigger(sbd_plan* p, TrigArgs& a)
 {
@@ -1241,63 +1277,26 @@ int launch_trigger(sbd_plan* p, TrigArgs& a)
   auto kern = k_trigger<VARIANT, TX, TY, NT, GEN>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+  a.nws = p->d_nws;
+  a.nwd = p->d_nwd;
   if (!GEN) {
     if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
     kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();
-    if (p->timing) { CK(cudaEventRecord(p->ev[1], p->stream)); }
+    if (p->timing) { CK(cudaEventRecord(p->ev[1], p->stream)); CK(cudaEventRecord(p->ev[2], p->stream)); }
     CK(cudaGetLastError());
     return SBD_OK;
   }
-  const bool vec = p->n_quads > 0 && a.prm.level_scan == 0 && (((uintptr_t)a.p) & 15) == 0;
-  if (!vec) {
-    // scalar path (nx*ny not a multiple of 4, unaligned p, or the UM early-exit scan): in order
-    if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
-    kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();
-    if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
-    if (p->n_coastal > 0) {
-      k_scan_trigger<14><<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
-    }
-    if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
-    CK(cudaGetLastError());
-    return SBD_OK;
-  }
-  // window kernel, then the level-scan kernel as its programmatic dependent: the scan's CTAs
-  // start streaming p as soon as SM resources allow (the window kernel signals
-  // launch_dependents on entry) and only wait for n_thc in their epilogue.
-  constexpr int QNT = 128;
-  static int G = 0;
-  if (!G) {
-    const char* e = getenv("SBD_SCAN_G");
-    G = e ? atoi(e) : 10;
-    if (G != 5 && G != 7 && G != 10 && G != 14) G = 10;
-    CK(cudaFuncSetAttribute(k_scan_quad<5, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 5 * QNT * 16));
-    CK(cudaFuncSetAttribute(k_scan_quad<7, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 7 * QNT * 16));
-    CK(cudaFuncSetAttribute(k_scan_quad<10, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 10 * QNT * 16));
-    CK(cudaFuncSetAttribute(k_scan_quad<14, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 14 * QNT * 16));
-  }
-  const int qsmem = 2 * G * QNT * 16;
-  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
-  kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();
-  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
-  {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cdiv(p->n_quads, QNT));
-    cfg.blockDim = dim3(QNT);
-    cfg.dynamicSmemBytes = qsmem;
-    cfg.stream = p->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = p->timing ? 0 : 1;  // timed runs: kernels in isolation
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    const int* quads = p->d_quads;
-    int nq = p->n_quads;
-    if (G == 5) CK(cudaLaunchKernelEx(&cfg, k_scan_quad<5, QNT>, (const TrigArgs)a, quads, nq));
-    else if (G == 7) CK(cudaLaunchKernelEx(&cfg, k_scan_quad<7, QNT>, (const TrigArgs)a, quads, nq));
-    else if (G == 10) CK(cudaLaunchKernelEx(&cfg, k_scan_quad<10, QNT>, (const TrigArgs)a, quads, nq));
-    else CK(cudaLaunchKernelEx(&cfg, k_scan_quad<14, QNT>, (const TrigArgs)a, quads, nq));
-    LAUNCHED();
-  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = p->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = p->timing ? 0 : 1;  // timed runs: kernels in isolation
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, (const TrigArgs)a)); LAUNCHED();
   if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
   CK(cudaGetLastError());
   return SBD_OK;
@@ -1414,7 +1413,9 @@ int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, 
       cudaMalloc((void**)&p->d_carry, 5 * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_cnt, 4 * sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_idx, (size_t)nx * ny * sizeof(int)) != cudaSuccess ||
-      cudaMalloc((void**)&p->d_quads, ((size_t)nx * ny / 4 + 1) * sizeof(int)) != cudaSuccess) {
+      cudaMalloc((void**)&p->d_quads, ((size_t)nx * ny / 4 + 1) * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_nws, (size_t)nx * ny * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_nwd, (size_t)nx * ny * sizeof(float)) != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "cudaMalloc of plan planes failed: %s", cudaGetErrorString(cudaGetLastError()));
     sbd_plan_destroy(p);
     return SBD_ECUDA;
@@ -1428,7 +1429,7 @@ void sbd_plan_destroy(sbd_plan* p)
   if (!p) return;
   if (p->own_stream) cudaStreamSynchronize(p->own_stream);
   cudaFree(p->d_gzsm); cudaFree(p->d_code); cudaFree(p->d_stats); cudaFree(p->d_carry); cudaFree(p->d_cnt);
-  cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads);
+  cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads); cudaFree(p->d_nws); cudaFree(p->d_nwd);
   for (int i = 0; i < 6; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   for (auto& s : p->stage) cudaFree(s.first);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
@@ -1454,8 +1455,12 @@ int sbd_plan_last_timing(sbd_plan* p, float* ms3)
   if (!p || !ms3 || !p->ev[0]) return fail(SBD_EINVAL, "timing was not enabled");
   ms3[0] = ms3[1] = ms3[2] = 0.0f;
   CK(cudaStreamSynchronize(p->stream));
-  CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));  // window kernel
-  if (p->variant == SBD_VARIANT_GENERIC) CK(cudaEventElapsedTime(&ms3[1], p->ev[1], p->ev[2]));  // scan kernel
+  if (p->variant == SBD_VARIANT_GENERIC) {
+    CK(cudaEventElapsedTime(&ms3[1], p->ev[0], p->ev[1]));  // level-scan kernel
+    CK(cudaEventElapsedTime(&ms3[0], p->ev[1], p->ev[2]));  // window + threshold kernel
+  } else {
+    CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));
+  }
   return SBD_OK;
 }
 int sbd_plan_use_own_stream(sbd_plan* p)
@@ -1564,23 +1569,39 @@ static int six_hourly_flag(int step, float timestep_s, float target_time)
   return sbd_modulo((float)step * timestep_s, target_time) < 0.0001f ? 1 : 0;  // G:264
 }
 
-int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const float* u, const float* v,
-                  const float* theta, float* ws, float* wd, float* thc, float* sb, uint8_t* flags)
+int sbd_plan_step_scan(sbd_plan* p, const float* pp, const float* u, const float* v)
 {
   if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
   if (!p->have_static) return fail(SBD_EINVAL, "sbd_plan_set_static has not been called");
-  if (!pp || !u || !v || !theta || !ws || !wd || !thc || !sb) return fail(SBD_EINVAL, "NULL argument");
-  const size_t n2 = (size_t)p->nx * p->ny, n3 = n2 * p->nz, nh = plane_elems(p);
+  if (!pp || !u || !v) return fail(SBD_EINVAL, "NULL argument");
+  const size_t n3 = (size_t)p->nx * p->ny * p->nz;
   p->stage_used = 0;
-  std::vector<OutView> pend;
   TrigArgs a{};
   int rc;
-  const bool any_host = !is_device_ptr(pp) || !is_device_ptr(theta) || !is_device_ptr(u) || !is_device_ptr(v);
   if ((rc = in_view(p, pp, n3, &a.p, true))) return rc;
   if ((rc = in_view(p, u, n3, &a.u, true))) return rc;
   if ((rc = in_view(p, v, n3, &a.v, true))) return rc;
+  a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny;
+  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  p->cur_p = a.p; p->cur_u = a.u; p->cur_v = a.v;
+  if ((rc = launch_scan(p, a))) return rc;
+  p->scan_done = true;
+  return SBD_OK;
+}
+
+int sbd_plan_step_finish(sbd_plan* p, float timestep, int step, const float* theta, float* ws, float* wd,
+                         float* thc, float* sb, uint8_t* flags)
+{
+  if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
+  if (!p->scan_done) return fail(SBD_EINVAL, "sbd_plan_step_scan has not been called for this step");
+  if (!theta || !ws || !wd || !thc || !sb) return fail(SBD_EINVAL, "NULL argument");
+  const size_t n2 = (size_t)p->nx * p->ny, nh = plane_elems(p);
+  std::vector<OutView> pend;
+  TrigArgs a{};
+  int rc;
+  a.p = p->cur_p; a.u = p->cur_u; a.v = p->cur_v;
+  bool any_host = !is_device_ptr(theta);
   if ((rc = in_view(p, theta, nh, &a.theta))) return rc;
-  const bool first = step < 2;
   void* d;
   if ((rc = out_view(p, ws, n2 * 4, true, &d, pend))) return rc; a.ws = (float*)d;
   if ((rc = out_view(p, wd, n2 * 4, true, &d, pend))) return rc; a.wd = (float*)d;
@@ -1588,11 +1609,20 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
   if ((rc = out_view(p, sb, n2 * 4, false, &d, pend))) return rc; a.sb = (float*)d;
   if ((rc = out_view(p, flags, n2, false, &d, pend))) return rc; a.flags = (uint8_t*)d;
   a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny;
-  a.first_step = first ? 1 : 0;
+  a.first_step = step < 2 ? 1 : 0;
   a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
   a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  p->scan_done = false;
   if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
   return flush_out(p, pend, any_host);
+}
+
+int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const float* u, const float* v,
+                  const float* theta, float* ws, float* wd, float* thc, float* sb, uint8_t* flags)
+{
+  int rc = sbd_plan_step_scan(p, pp, u, v);
+  if (rc) return rc;
+  return sbd_plan_step_finish(p, timestep, step, theta, ws, wd, thc, sb, flags);
 }
 
 int sbd_plan_step_py(sbd_plan* p, int step, float timestep_min, const float* pp, const float* u,

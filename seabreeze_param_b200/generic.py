@@ -168,6 +168,18 @@ class Plan:
                                            q(theta), q(windspeed), q(winddir), q(thc), q(sb_con), q(flags)),
                     "plan_step")
 
+    def step_scan(self, p, u, v):
+        """First half of step(): the level scan over p (needs neither theta nor halos)."""
+        q = _capi.ptr
+        _capi.check(self.lib.sbd_plan_step_scan(self._h, q(p), q(u), q(v)), "plan_step_scan")
+
+    def step_finish(self, timestep, timestep_number, theta, windspeed, winddir, thc, sb_con, flags=None):
+        """Second half of step(): window sums on theta (halos valid), thresholds, state update."""
+        q = _capi.ptr
+        _capi.check(self.lib.sbd_plan_step_finish(self._h, float(timestep), int(timestep_number), q(theta),
+                                                  q(windspeed), q(winddir), q(thc), q(sb_con), q(flags)),
+                    "plan_step_finish")
+
     def step_py(self, timestep_number, timestep_min, p, u, v, theta, windspeed, winddir, output, flags=None):
         q = _capi.ptr
         _capi.check(self.lib.sbd_plan_step_py(self._h, int(timestep_number), float(timestep_min), q(p), q(u),

@@ -18,24 +18,43 @@ from . import _capi
 
 
 class RowBlockHalo:
-    def __init__(self, nx, ny_local, h, rank=0, world=1, device=None, group=None):
+    def __init__(self, nx, ny_local, h, rank=0, world=1, device=None, group=None, chain_fn=None):
         self.nx, self.ny, self.h = nx, ny_local, h
         self.rank, self.world = rank, world
         self.device = device
         self.group = group
-        self.lib = _capi.load()
+        self.lib = None
+        self.chain_fn = chain_fn  # tests inject a host implementation of the carry chain (gloo, CPU)
         self.up = rank - 1 if rank > 0 else None       # owns the rows above (smaller latitude index)
         self.down = rank + 1 if rank < world - 1 else None
         self.ns_mask = (1 if self.up is None else 0) | (2 if self.down is None else 0)
         self.launches_per_step = 1
 
     # -- halo fill of one halo'd field (torch CUDA tensor, (ny+2h, nx+2h), contiguous float32) --
-    def swap_bounds(self, field):
+    def _local_fill(self, field):
+        """East-west periodic wrap on every row, edge-row replication on the domain's own north /
+        south edges.  CUDA tensors: one kernel (sbd_swap_bounds_dev_f32).  CPU tensors (only the
+        gloo tests of the exchange logic use them): the same pure data movement by slicing."""
+        h, ny, nx = self.h, self.ny, self.nx
+        if field.is_cuda:
+            import torch
+            if self.lib is None:
+                self.lib = _capi.load()
+            stream = torch.cuda.current_stream(field.device).cuda_stream
+            _capi.check(self.lib.sbd_swap_bounds_dev_f32(field.data_ptr(), nx, ny, h, self.ns_mask, stream),
+                        "swap_bounds")
+            return
         import torch
+        idx = (torch.arange(-h, nx + h) % nx) + h
+        field[h:h + ny, :] = field[h:h + ny, :][:, idx]
+        if self.ns_mask & 1:
+            field[0:h, :] = field[h:h + 1, :]
+        if self.ns_mask & 2:
+            field[ny + h:, :] = field[ny + h - 1:ny + h, :]
+
+    def swap_bounds(self, field):
         h, ny = self.h, self.ny
-        stream = torch.cuda.current_stream(field.device).cuda_stream
-        _capi.check(self.lib.sbd_swap_bounds_dev_f32(field.data_ptr(), self.nx, ny, h, self.ns_mask, stream),
-                    "swap_bounds")
+        self._local_fill(field)
         if self.world > 1:
             import torch.distributed as dist
             ops = []
@@ -71,8 +90,13 @@ class RowBlockHalo:
                 dist.recv(buf, self.up, group=self.group)
                 carry = buf.cpu().numpy().copy()
             first = 1 if (self.up is None and pass_no == 0) else 0
-            _capi.check(self.lib.sbd_stats_chain_f32(interior, nx, ny, ldx, pass_no, first, carry.ctypes.data),
-                        "stats_chain")
+            if self.chain_fn is not None:
+                carry = self.chain_fn(sigma_h, pass_no, first, carry)
+            else:
+                if self.lib is None:
+                    self.lib = _capi.load()
+                _capi.check(self.lib.sbd_stats_chain_f32(interior, nx, ny, ldx, pass_no, first, carry.ctypes.data),
+                            "stats_chain")
             if self.down is not None:
                 dist.send(torch.from_numpy(carry).to(dev), self.down, group=self.group)
             # the last rank holds the global carry: broadcast it

@@ -426,6 +426,269 @@ __global__ void k_stats_seq(const float* __restrict__ ary, int nx, int ny, int l
     else carry[1] = acc;
   }
 }
+// ------------------------------------------------------------------------------------------------
+// K3' stats, exact and parallel.  The reference accumulates `s = s + x_i` sequentially in fp32
+// (G:466, G:471-475); the rounding of every step depends on the running sum, so a tree reduction is
+// not bit-compatible.  For x_i >= 0 the chain is nevertheless parallelisable
+// exactly: while s stays inside one binade [2^e, 2^(e+1)) every step is an integer addition
+//     n <- n + q_i (+1 if x_i lies exactly half-way and n + q_i is odd),  s = n * ulp(e),
+// with q_i = x_i / ulp rounded to nearest.  The half-way rule composes as a 3-field monoid
+// (A, T, B): n -> n + A without a tie, n -> roundup_even(n + A) + B once a tie has fixed the
+// parity.  One CTA scans a tile of 8192 elements with that monoid, locates the first element at
+// which the sum would leave the binade (or a negative / non-finite element), applies the prefix up to
+// there in one go, performs that one addition as the reference does (a real fp32 add), and
+// continues behind it in the new binade.  A whole array costs (#tiles + #binades crossed)
+// block-scans instead of N dependent adds.
+// ------------------------------------------------------------------------------------------------
+struct TieMon { unsigned long long A, B; int T; };
+__device__ __forceinline__ TieMon tm_combine(const TieMon& l, const TieMon& r)  // l first, then r
+{
+  TieMon o;
+  if (!l.T) { o.A = l.A + r.A; o.T = r.T; o.B = r.B; }
+  else if (!r.T) { o.A = l.A; o.T = 1; o.B = l.B + r.A; }
+  else { const unsigned long long m = l.B + r.A; o.A = l.A; o.T = 1; o.B = m + (m & 1ull) + r.B; }
+  return o;
+}
+__device__ __forceinline__ unsigned long long tm_apply(const TieMon& m, unsigned long long n)
+{
+  if (!m.T) return n + m.A;
+  unsigned long long t = n + m.A;
+  t += (t & 1ull);
+  return t + m.B;
+}
+__device__ __forceinline__ TieMon tm_shfl_up(const TieMon& m, int d)
+{
+  TieMon o;
+  o.A = __shfl_up_sync(0xffffffffu, m.A, d);
+  o.B = __shfl_up_sync(0xffffffffu, m.B, d);
+  o.T = __shfl_up_sync(0xffffffffu, m.T, d);
+  return o;
+}
+// contribution of x to a sum whose binade has biased exponent es (>= 1; 1 also covers denormals)
+__device__ __forceinline__ TieMon tm_classify(float x, int es, bool& bad)
+{
+  TieMon m; m.A = 0; m.B = 0; m.T = 0;
+  const uint32_t ux = __float_as_uint(x);
+  int ex = (int)((ux >> 23) & 0xffu);
+  const uint32_t fr = ux & 0x7fffffu;
+  if ((ux >> 31) && (ux << 1)) { bad = true; return m; }   // negative (not -0): generic path
+  if (ex == 255) { bad = true; return m; }                 // Inf / NaN
+  const uint32_t mx = ex ? (fr | 0x800000u) : fr;
+  if (ex == 0) ex = 1;
+  const int d = es - ex;
+  if (d <= 0) {
+    m.A = (-d >= 3) ? (1ull << 26) : ((unsigned long long)mx << (-d));  // >= 2^24 forces a crossing
+  } else if (d < 25) {
+    const uint32_t q0 = mx >> d, rem = mx & ((1u << d) - 1u), half = 1u << (d - 1);
+    if (rem > half) m.A = q0 + 1u;
+    else { m.A = q0; m.T = (rem == half) ? 1 : 0; }
+  }
+  return m;
+}
+
+constexpr int ST_NT = 1024, ST_E = 8, ST_TILE = ST_NT * ST_E;
+constexpr unsigned long long ST_LIM = (1ull << 24) - 2ull;  // stay strictly inside the binade
+
+__global__ void __launch_bounds__(ST_NT) k_stats_exact(const float* __restrict__ ary, int nx, int ny, int ld,
+                                                       int pass, int first, float* __restrict__ carry)
+{
+  __shared__ TieMon s_warp[32];
+  __shared__ unsigned long long s_nlast;
+  __shared__ int s_first_bad;
+  __shared__ float s_state;
+  __shared__ float s_xbad;
+  __shared__ float s_red[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n_total = (long long)nx * ny;
+  const float mean = carry[4];
+  if (tid == 0) s_state = (pass == 0) ? carry[0] : carry[1];
+  float mx = first ? -__int_as_float(0x7f800000) : carry[2];
+  float mn = first ? __int_as_float(0x7f800000) : carry[3];
+  __syncthreads();
+
+  for (long long tbase = 0; tbase < n_total; tbase += ST_TILE) {
+    // ---- load this thread's ST_E consecutive elements (row-pitched source) ----
+    float x[ST_E];
+    const long long e0 = tbase + (long long)tid * ST_E;
+    {
+      int y = (int)(e0 / nx), xx = (int)(e0 - (long long)y * nx);
+#pragma unroll
+      for (int j = 0; j < ST_E; ++j) {
+        float v = 0.0f;
+        const bool in = (e0 + j) < n_total;
+        if (in) {
+          v = ary[(size_t)y * ld + xx];
+          if (pass == 0) { mx = fmaxf(mx, v); mn = fminf(mn, v); }
+          else { const float d = v - mean; v = d * d; }   // G:473
+        }
+        x[j] = in ? v : 0.0f;   // +0 is the identity of the chain
+        if (++xx == nx) { xx = 0; ++y; }
+      }
+    }
+    const int tile_len = (int)min((long long)ST_TILE, n_total - tbase);
+    int pos = 0;  // elements [0,pos) of the tile are already folded into s_state
+    while (pos < tile_len) {
+      const float s = s_state;
+      const uint32_t us = __float_as_uint(s);
+      const int es_raw = (int)((us >> 23) & 0xffu);
+      if ((us >> 31) || es_raw == 255) {
+        // negative or non-finite running sum: plain sequential adds for the rest of the tile
+        __syncthreads();
+        if (tid == 0) s_first_bad = -2;
+        __syncthreads();
+      }
+      const bool generic_seq = (us >> 31) || es_raw == 255;
+      if (generic_seq) {
+        // every thread hands its elements to thread 0 through shared memory, 64 at a time
+        for (int b = pos; b < tile_len; b += 64) {
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < ST_E; ++j) {
+            const int gi = tid * ST_E + j;
+            if (gi >= b && gi < b + 64) s_red[gi - b] = x[j];
+          }
+          __syncthreads();
+          if (tid == 0) {
+            float acc = s_state;
+            const int cnt = min(64, tile_len - b);
+            for (int k = 0; k < cnt; ++k) acc = acc + s_red[k];
+            s_state = acc;
+          }
+        }
+        __syncthreads();
+        pos = tile_len;
+        break;
+      }
+      const int es = max(es_raw, 1);
+      const unsigned long long n0 = es_raw ? ((us & 0x7fffffu) | 0x800000u) : (us & 0x7fffffu);
+      if (n0 > ST_LIM) {
+        // the running sum sits on the last two representable values of its binade: take the next
+        // element with a real fp32 add (happens at most twice per binade)
+        const int owner = pos / ST_E, oj = pos - owner * ST_E;
+        __syncthreads();
+        if (tid == owner) {
+          float xb = 0.0f;
+#pragma unroll
+          for (int j = 0; j < ST_E; ++j) if (j == oj) xb = x[j];
+          s_state = s + xb;
+        }
+        __syncthreads();
+        pos = pos + 1;
+        continue;
+      }
+      // ---- per-thread monoid over its not-yet-consumed elements ----
+      TieMon el[ST_E];
+      bool bad[ST_E];
+      TieMon tot; tot.A = 0; tot.B = 0; tot.T = 0;
+      bool stop = false;  // elements behind a bad one contribute nothing to the scan
+#pragma unroll
+      for (int j = 0; j < ST_E; ++j) {
+        const int gi = tid * ST_E + j;
+        bad[j] = false;
+        el[j].A = 0; el[j].B = 0; el[j].T = 0;
+        if (gi >= pos && gi < tile_len) el[j] = tm_classify(x[j], es, bad[j]);
+        if (bad[j]) stop = true;
+        if (!stop) tot = tm_combine(tot, el[j]);
+      }
+      // ---- block-wide inclusive scan of the thread totals ----
+      TieMon inc = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const TieMon o = tm_shfl_up(inc, d);
+        if (lane >= d) inc = tm_combine(o, inc);
+      }
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        TieMon w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const TieMon o = tm_shfl_up(w, d);
+          if (lane >= d) w = tm_combine(o, w);
+        }
+        s_warp[lane] = w;
+        if (lane == 0) s_first_bad = 0x7fffffff;
+      }
+      __syncthreads();
+      TieMon excl; excl.A = 0; excl.B = 0; excl.T = 0;
+      if (warp > 0) excl = s_warp[warp - 1];
+      {
+        TieMon prev = tm_shfl_up(inc, 1);
+        if (lane > 0) excl = tm_combine(excl, prev);
+      }
+      // ---- walk own elements: first index where the sum leaves the binade or an element is bad ----
+      unsigned long long n = tm_apply(excl, n0);
+      int my_first = 0x7fffffff;
+      unsigned long long n_before[ST_E];
+      if (n > ST_LIM) my_first = -1;  // an earlier thread already crossed; its index wins the min
+#pragma unroll
+      for (int j = 0; j < ST_E; ++j) {
+        const int gi = tid * ST_E + j;
+        n_before[j] = n;
+        if (gi >= pos && gi < tile_len && my_first == 0x7fffffff) {
+          if (bad[j]) my_first = gi;
+          else {
+            const unsigned long long nn = tm_apply(el[j], n);
+            if (nn > ST_LIM) my_first = gi; else n = nn;
+          }
+        }
+      }
+      if (my_first >= 0 && my_first != 0x7fffffff) atomicMin(&s_first_bad, my_first);
+      if (tid == ST_NT - 1) s_nlast = n;
+      __syncthreads();
+      const int fb = s_first_bad;
+      if (fb == 0x7fffffff) {
+        // whole remainder of the tile stays in the binade: one integer update
+        if (tid == ST_NT - 1) {
+          const unsigned long long nf = s_nlast;
+          const uint32_t bits = (nf >= (1ull << 23)) ? (((uint32_t)es << 23) | (uint32_t)(nf & 0x7fffffull))
+                                                     : (uint32_t)nf;
+          s_state = __uint_as_float(bits);
+        }
+        __syncthreads();
+        pos = tile_len;
+      } else {
+        // prefix up to fb-1 in one go, then the offending addition exactly as the reference does it
+        const int owner = fb / ST_E, oj = fb - owner * ST_E;
+        if (tid == owner) {
+          unsigned long long nb = 0; float xb = 0.0f;
+#pragma unroll
+          for (int j = 0; j < ST_E; ++j) if (j == oj) { nb = n_before[j]; xb = x[j]; }
+          const uint32_t bits = (nb >= (1ull << 23)) ? (((uint32_t)es << 23) | (uint32_t)(nb & 0x7fffffull))
+                                                     : (uint32_t)nb;
+          s_state = __uint_as_float(bits) + xb;   // the reference's fp32 add
+          s_xbad = xb;
+        }
+        __syncthreads();
+        pos = fb + 1;
+      }
+    }
+  }
+  // ---- max / min are order-free ----
+  if (pass == 0) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    __syncthreads();
+    if (lane == 0) { s_red[warp] = mx; s_red[32 + warp] = mn; }
+    __syncthreads();
+    if (warp == 0) {
+      mx = s_red[lane]; mn = s_red[32 + lane];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+    }
+  }
+  if (tid == 0) {
+    if (pass == 0) { carry[0] = s_state; carry[2] = mx; carry[3] = mn; }
+    else carry[1] = s_state;
+  }
+}
+
 // stats[0]=mean (from sum), then after pass 1: stats[1]=2/sqrt(var/n), stats[2]=(max-min)/4, stats[3]=var
 __global__ void k_stats_finish(float* __restrict__ carry, float fn, int stage, float* __restrict__ stats)
 {
@@ -1158,13 +1421,25 @@ int flush_out(sbd_plan* p, std::vector<OutView>& pend, bool any_host)
   return SBD_OK;
 }
 
+// SBD_STATS_SEQ=1 selects the plain sequential chain (k_stats_seq) instead of the exact parallel
+// formulation (k_stats_exact); both produce the reference's bits, the tests compare them.
+void launch_stats_pass(cudaStream_t st, const float* d_ary, int nx, int ny, int ld, int pass, int first,
+                       float* d_carry)
+{
+  static int seq = -1;
+  if (seq < 0) { const char* e = getenv("SBD_STATS_SEQ"); seq = (e && atoi(e)) ? 1 : 0; }
+  if (seq) k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, pass, first, d_carry);
+  else k_stats_exact<<<1, ST_NT, 0, st>>>(d_ary, nx, ny, ld, pass, first, d_carry);
+  LAUNCHED();
+}
+
 int run_stats(cudaStream_t st, const float* d_ary, int nx, int ny, int ld, float* d_carry, float* d_stats)
 {
   const float fn = (float)(nx * ny);  // real(nlons*nlats)
   CK(cudaMemsetAsync(d_carry, 0, 5 * sizeof(float), st));  // running sum starts at +0 (G:466)
-  k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, 0, 1, d_carry); LAUNCHED();
+  launch_stats_pass(st, d_ary, nx, ny, ld, 0, 1, d_carry);
   k_stats_finish<<<1, 1, 0, st>>>(d_carry, fn, 0, d_stats); LAUNCHED();
-  k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, 1, 0, d_carry); LAUNCHED();
+  launch_stats_pass(st, d_ary, nx, ny, ld, 1, 0, d_carry);
   k_stats_finish<<<1, 1, 0, st>>>(d_carry, fn, 1, d_stats); LAUNCHED();
   CK(cudaGetLastError());
   return SBD_OK;
@@ -1862,7 +2137,7 @@ int sbd_stats_chain_f32(const float* ary, int nx, int ny, int ld, int pass, int 
   if ((rc = t.in(ary, (size_t)ld * (ny - 1) + nx, &d_ary))) return rc;
   if ((rc = t.scratch(5 * 4, &d_carry))) return rc;
   CK(cudaMemcpyAsync(d_carry, carry5, 20, cudaMemcpyHostToDevice, t.st));
-  k_stats_seq<<<1, 32, 0, t.st>>>(d_ary, nx, ny, ld, pass, first, (float*)d_carry); LAUNCHED();
+  launch_stats_pass(t.st, d_ary, nx, ny, ld, pass, first, (float*)d_carry);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(carry5, d_carry, 20, cudaMemcpyDeviceToHost, t.st));
   return t.finish();

@@ -70,6 +70,34 @@ def test_sigmoid_sequential_stats(oracle):
         assert_bits_equal(F(sm_o), seabreeze.sigmoid(F(a)), "f2py sigmoid")
 
 
+def test_exact_parallel_stats_adversarial(oracle):
+    """k_stats_exact (parallel, monoid scan) must reproduce the sequential fp32 chain bit-for-bit on
+    inputs built to hit ties (round-half-even), binade crossings, zeros, denormals, huge jumps,
+    negatives and non-finite values."""
+    rng = np.random.default_rng(21)
+    cases = {}
+    cases["integers (ties everywhere)"] = rng.integers(0, 5, (300, 301)).astype(np.float32)
+    cases["halves"] = (rng.integers(0, 9, (257, 129)) * 0.5).astype(np.float32)
+    cases["sparse land (70% zeros)"] = (rng.random((400, 513)) * 300 * (rng.random((400, 513)) > 0.7)).astype(np.float32)
+    a = rng.random((97, 1031)).astype(np.float32); a[0, :50] = 0; a[40, 7] = 3.0e7; a[41, 9] = 1.0e-30
+    cases["jumps + tiny"] = a
+    cases["denormals"] = (rng.random((33, 65)) * 1e-41).astype(np.float32)
+    b = (rng.random((64, 200)) * 10).astype(np.float32); b[10, 10] = -3.5; b[50, 3] = -0.0
+    cases["negatives"] = b
+    c = (rng.random((40, 50)) * 10).astype(np.float32); c[20, 20] = np.inf
+    cases["inf"] = c
+    cases["powers of two"] = (2.0 ** rng.integers(-3, 12, (150, 150))).astype(np.float32)
+    cases["one cell"] = np.array([[7.25]], np.float32)
+    # 6.48 M cells: the running sum parks on the last value of a binade (regression: n0 > limit)
+    cases["0.1 degree grid size"] = (rng.random((1800, 3600)) * 300 * (rng.random((1800, 3600)) > 0.7)).astype(np.float32)
+    for nm, arr in cases.items():
+        sm_o, st_o = oracle.sigmoid(arr)
+        st_g = np.zeros(4, np.float32)
+        sm_g = generic.sigmoid(arr, stats=st_g)
+        assert_bits_equal(st_o, st_g, "stats: " + nm)
+        assert_bits_equal(sm_o, sm_g, "sigmoid: " + nm)
+
+
 @pytest.mark.parametrize("name", ["t_py", "c5"])
 def test_py_diag_time_loop(oracle, name):
     cfg = synth.CONFIGS[name]

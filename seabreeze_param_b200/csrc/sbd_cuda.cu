@@ -900,12 +900,12 @@ __device__ __forceinline__ void window_fixed(const float* __restrict__ s_t0, con
 //   SPLIT (generic): n_thc is stored to thc[] (state update G:262); level search + thresholds
 //            run in k_scan_quad / k_final.  Otherwise (python: one global level) the thresholds
 //            are applied here.
-template <int VARIANT, int TX, int TY, int NT, bool SPLIT>
+template <int VARIANT, int TX, int TY, int NT, int RMAX, bool SPLIT>
 __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
 {
   constexpr int CPT = TX * TY / NT;  // cells per thread in phase 2
   constexpr int NB = 64;             // nn buckets: 1..NB-2 exact, NB-1 = "wider than the tile halo"
-  static_assert(TX % 32 == 0 && NT % TX == 0 && (TX * TY) % NT == 0, "tile shape");
+  static_assert(TX % 32 == 0 && NT % TX == 0 && (TX * TY) % NT == 0 && TX * TY <= 65536 && RMAX < 63, "tile shape");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = a.R;
   const int W = TX + 2 * R, Hh = TY + 2 * R;
@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
 
   // ---- phase 1 ----  one warp per staged row, all loads of a row in flight together
   {
-    constexpr int MAXC = (TX + 2 * 16 + 31) / 32;  // R <= 16 for this tile shape
+    constexpr int MAXC = (TX + 2 * RMAX + 31) / 32;  // R <= RMAX for this tile shape
     const int warp = tid >> 5, lane = tid & 31;
     for (int ly = warp; ly < Hh; ly += NT / 32) {
       float th[MAXC], gz[MAXC];
@@ -1541,15 +1541,14 @@ int launch_scan(sbd_plan* p, TrigArgs& a)
 
 // window kernel (+ thresholds).  Generic: launched as the programmatic dependent of the scan kernel
 // that precedes it in the stream.
-template <int VARIANT>
-int launch_trigger(sbd_plan* p, TrigArgs& a)
+template <int VARIANT, int TX, int TY, int NT, int RMAX>
+int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
 {
-  constexpr int TX = 64, TY = 16, NT = 256;
   constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
   const int R = a.R;
   const size_t cells = (size_t)(TX + 2 * R) * (TY + 2 * R);
   const size_t smem = cells * 4 + ((size_t)(TY + 2 * R) * ((TX + 2 * R + 31) / 32) + 2) * 4 + (size_t)TX * TY * 4;
-  auto kern = k_trigger<VARIANT, TX, TY, NT, GEN>;
+  auto kern = k_trigger<VARIANT, TX, TY, NT, RMAX, GEN>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
   a.nws = p->d_nws;
@@ -1575,6 +1574,17 @@ int launch_trigger(sbd_plan* p, TrigArgs& a)
   if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
   CK(cudaGetLastError());
   return SBD_OK;
+}
+
+// window kernel (+ thresholds).  Generic: launched as the programmatic dependent of the scan kernel
+// that precedes it in the stream.  Two tile shapes: 64x16 cells with a halo of up to 16 (coarse
+// grids: N512, 0.1 degree, ERA-Interim) and 128x64 cells with a halo of up to 56 (km-scale grids,
+// where the search radius reaches k+1 = 55 cells).
+template <int VARIANT>
+int launch_trigger(sbd_plan* p, TrigArgs& a)
+{
+  if (a.R <= 16) return launch_trigger_cfg<VARIANT, 64, 16, 256, 16>(p, a);
+  return launch_trigger_cfg<VARIANT, 128, 64, 1024, 56>(p, a);
 }
 
 int ensure_device()
@@ -1825,7 +1835,7 @@ int sbd_plan_set_static(sbd_plan* p, const float* mask, const float* z, const fl
   p->n_coastal = cnt[1];
   p->n_quads = cnt[3];
   if (cnt[2] != cnt[1]) return fail(SBD_ECUDA, "internal: compaction count differs from the coastal-cell count");
-  p->R = min(p->nn_max, 16);
+  p->R = (p->nn_max <= 16) ? p->nn_max : min(p->nn_max, 56);  // see launch_trigger
   p->have_static = true;
   return SBD_OK;
 }

@@ -231,23 +231,30 @@ def test_generic_device_pointers_torch(oracle):
     plan.close()
 
 
-def test_large_window_fallback_path(oracle):
-    """Cells whose final search radius exceeds the shared-memory tile halo take the global-memory
-    path; a blocky mask with a wide halo forces nn > 16."""
-    cfg = synth.Config("t_big", 160, 96, 4, 24, "generic", 14.0, True, 1440.0, "wide-window test")
+@pytest.mark.parametrize("nx,ny,h,filt,expect", [(160, 96, 24, 14.0, "big tile"), (320, 240, 54, 40.0, "big tile"),
+                                                   (300, 200, 72, 60.0, "global path")])
+def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect):
+    """km-scale regional grids (config 3): the final search radius reaches tens of cells.  Radii up to
+    16 use the 64x16 tile, up to 56 the 128x64 tile, beyond that the global-memory path."""
+    cfg = synth.Config("t_big", nx, ny, 4, h, "generic", filt, True, 1440.0, "wide-window test")
     case = generic_case(cfg, oracle)
-    ny, nx = cfg.ny, cfg.nx
     plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
     plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
-    assert plan.info()["nn_max"] > 16, plan.info()
+    nn_max = plan.info()["nn_max"]
+    assert nn_max > 16, plan.info()
+    if expect == "global path":
+        assert nn_max > 56, plan.info()
     so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
     sp = [np.zeros((ny, nx), np.float32) for _ in range(4)]
-    theta_h, p, u, v = generic_step_inputs(cfg, case, 1, oracle)
-    oracle.seabreeze_diag(cfg.timestep, 1, p, u, v, theta_h, case["mask_h"], case["z_h"], case["sigma_h"],
-                          *so, cfg.h, literal=False)
-    plan.step(cfg.timestep, 1, p, u, v, theta_h, *sp)
-    for a, b, nm in zip(so, sp, ("windspeed", "winddir", "thc", "sb_con")):
-        assert_bits_equal(a, b, nm)
+    for step in (1, 2):
+        theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
+        fo = oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"], case["sigma_h"],
+                                   *so, cfg.h, literal=False)
+        fp = np.zeros((ny, nx), np.uint8)
+        plan.step(cfg.timestep, step, p, u, v, theta_h, *sp, flags=fp)
+        for a, b, nm in zip(so, sp, ("windspeed", "winddir", "thc", "sb_con")):
+            assert_bits_equal(a, b, "%s step %d" % (nm, step))
+        assert np.array_equal(fo, fp)
     plan.close()
 
 

@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "grid_cells_per_sec_per_timestep"
 UNIT = "cells/s"
-NSETS = 4  # rotating input sets: 4 x 661 MB of p,u,v >> 126 MB L2
+NSETS = int(os.environ.get("BENCH_NSETS", "4"))  # rotating input sets: 4 x 661 MB of p,u,v >> 126 MB L2
 
 
 def measured_peak():

@@ -803,6 +803,8 @@ struct TrigArgs {
   // generic: wind speed / direction at the selected level, written by the level-scan kernel and
   // consumed by the window kernel's threshold stage (plan-owned scratch planes, nx x ny)
   float* nws; float* nwd;
+  int order;  // 0: scan -> window -> final (multi-GPU friendly); 1: window -> scan(+thresholds)
+  int dbg;  // profiling experiments only (SBD_DBG): bit0 skip window sums, bit1 skip thresholds, bit2 skip staging
 };
 
 template <int VARIANT>
@@ -860,6 +862,31 @@ __device__ __forceinline__ void trigger_point(const TrigArgs& a, size_t c, size_
     a.out[2 * n2 + c] = ws;                                               // P:279
     a.out[3 * n2 + c] = wd;                                               // P:280
   }
+  if (a.flags) a.flags[c] = fl;
+}
+
+// generic-variant thresholds with the previous windspeed / winddir already in registers
+__device__ __forceinline__ void trigger_point_vals(const TrigArgs& a, size_t c, float n_thc, float n_ws,
+                                                   float n_wd, float ws_prev, float wd_prev)
+{
+  float ws = ws_prev, wd = wd_prev;
+  if (a.first_step) { ws = n_ws; wd = n_wd; }                             // G:235-239
+  const float thc_abs = fabsf(n_thc);                                     // G:242
+  const float mws = (ws + n_ws) / 2.0f;                                   // G:243
+  const float dws = fabsf(ws - n_ws);                                     // G:244
+  const float dwd = fabsf(sbd_modulo((wd - n_wd) + 180.0f, 360.0f) - 180.0f);  // G:246-247
+  float sb = 0.0f;                                                        // G:258
+  uint8_t fl = 1;
+  if (dwd < a.prm.thresh_winddir && dws < a.prm.thresh_windch && mws < a.prm.thresh_wind &&
+      thc_abs > a.prm.thresh_thc) {                                       // G:249-252
+    const float scale_wind = (a.prm.thresh_wind - mws) / fmaxf(1.0f, mws);  // G:254
+    const float scale_thc = (thc_abs - a.prm.thresh_thc) / n_thc;           // G:255
+    sb = scale_thc * scale_wind;                                             // G:256
+    fl = 3;
+  }
+  a.sb[c] = sb;
+  a.ws[c] = n_ws;                                                         // G:261
+  if (a.six_hourly || a.first_step) a.wd[c] = n_wd;                       // G:237, G:264-266
   if (a.flags) a.flags[c] = fl;
 }
 
@@ -923,6 +950,9 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int tid = threadIdx.x;
 
+  // order 1: the level scan follows as a programmatic dependent and may start right away
+  if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
+
   if (tid < NB) s_cnt[tid] = 0;
   // ---- python: one pressure level for the whole grid (P:228), first minimum of |p - target| ----
   if (VARIANT == SBD_VARIANT_PYTHON && tid == NT - 1) {
@@ -939,7 +969,7 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
   {
     constexpr int MAXC = (TX + 2 * RMAX + 31) / 32;  // R <= RMAX for this tile shape
     const int warp = tid >> 5, lane = tid & 31;
-    for (int ly = warp; ly < Hh; ly += NT / 32) {
+    for (int ly = warp; ly < ((a.dbg & 4) ? 0 : Hh); ly += NT / 32) {
       float th[MAXC], gz[MAXC];
       uint32_t cd[MAXC];
 #pragma unroll
@@ -1017,7 +1047,6 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
   n_list = s_off[NB - 1] + s_cnt[NB - 1];
 
   // ---- phase 3 ----
-  bool waited = false;
   for (int e = tid; e < n_list; e += NT) {
     const uint32_t ent = s_list[e];
     const int lid = (int)(ent & 0xffffu);
@@ -1029,7 +1058,9 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
     int nn = bkt;
     float T_l = 0.0f, T_s = 0.0f;
     uint32_t c_l = 0, c_s = 0;
-    if (bkt != NB - 1) {
+    if (a.dbg & 1) {
+      T_l = 1.0f; T_s = 2.0f; c_l = 1; c_s = 1;
+    } else if (bkt != NB - 1) {
       const int lcx = R + lx, lcy = R + ly;
       switch (nn) {
         case 1: window_fixed<1>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
@@ -1075,12 +1106,10 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
     const float n_thc = mul * ((T_l / n_l) - (T_s / n_s));      // G:216
     const size_t c = (size_t)gy * a.g.nx + gx;
     if (SPLIT) {
-      // generic: the level scan (k_scan_quad / k_scan_scalar) is the kernel launched just before
-      // this one; this grid is its programmatic dependent, so everything up to here overlapped
-      // with it.  Wait for its n_ws / n_wd, then thresholds + state update (G:235-266).
-      if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
-      a.thc[c] = n_thc;                                         // G:262
-      trigger_point<VARIANT>(a, c, n2, n_thc, __ldcg(a.nws + c), __ldcg(a.nwd + c), 0.0f);
+      // generic: n_thc goes straight into the caller's thc array (state update G:262); the
+      // thresholds are applied by k_final once the level scan has delivered n_ws / n_wd.  This
+      // grid never waits for the scan, so its CTAs retire while the scan is still streaming.
+      a.thc[c] = n_thc;
     } else if (VARIANT == SBD_VARIANT_PYTHON) {
       const int lev = s_lev;
       const float uu = __ldg(a.u + (size_t)lev * n2 + c), vv = __ldg(a.v + (size_t)lev * n2 + c);
@@ -1212,11 +1241,26 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
   };
 
   issue(0);
-  // the window kernel launched next in the stream may start now (programmatic dependent launch);
-  // it waits for this grid only before it reads n_ws / n_wd
-  asm volatile("griddepcontrol.launch_dependents;");
+  // order 0: the window kernel launched next in the stream may start now (programmatic dependent)
+  if (a.order == 0) asm volatile("griddepcontrol.launch_dependents;");
+  // Everything the epilogue needs that does not depend on the scan is requested now, so that it
+  // arrives under the pressure stream: which cells of the quad are coastal (static code plane),
+  // and (order 1) the previous windspeed / winddir of the quad as 16-byte loads.
+  uint32_t cdq[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j;
+    const int y = c / a.g.nx, x = c - y * a.g.nx;
+    cdq[j] = a.code[(size_t)(y + a.g.h) * a.g.ldx + (x + a.g.h)];
+  }
+  float4 ws4 = make_float4(0.f, 0.f, 0.f, 0.f), wd4 = ws4;
+  if (a.order == 1 && !a.first_step) {
+    ws4 = __ldcg(reinterpret_cast<const float4*>(a.ws) + m);
+    wd4 = __ldcg(reinterpret_cast<const float4*>(a.wd) + m);
+  }
   float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
   int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+  int pf_lev = -1;
   for (int g = 0; g < ngroups; ++g) {
     if (g + 1 < ngroups) {
       issue(g + 1);
@@ -1239,15 +1283,17 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
         if (kk == 0 || e3 < b3) { b3 = e3; l3 = kk; }
       }
     }
+    // speculative L2 prefetch of u,v at the best level so far: for a monotone pressure column the
+    // minimum is final long before the last group, and the epilogue's loads then hit L2
+    if (l0 != pf_lev) {
+      pf_lev = l0;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(a.u + (size_t)l0 * n2) + m));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(a.v + (size_t)l0 * n2) + m));
+    }
   }
-  // which cells of the quad are in the coastal zone (static code plane, L2 resident)
   bool act[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + j;
-    const int y = c / a.g.nx, x = c - y * a.g.nx;
-    act[j] = (a.code[(size_t)(y + a.g.h) * a.g.ldx + (x + a.g.h)] & 0x7fffu) != 0;
-  }
+  for (int j = 0; j < 4; ++j) act[j] = (cdq[j] & 0x7fffu) != 0;
   // wind at the selected levels: all loads first
   const int lv[4] = {l0, l1, l2, l3};
   float uu[4], vv[4];
@@ -1266,6 +1312,19 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
   float nws[4], nwd[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) wind_from_uv(a, uu[j], vv[j], nws[j], nwd[j]);
+  if (a.order == 1) {
+    // this grid is the programmatic dependent of the window kernel: wait for its n_thc, then
+    // thresholds, scaling and state update right here (G:235-266) -- no further kernel
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.thc) + m);
+    const float thc_[4] = {thc4.x, thc4.y, thc4.z, thc4.w};
+    const float wsp[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
+    const float wdp[4] = {wd4.x, wd4.y, wd4.z, wd4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (act[j]) trigger_point_vals(a, (size_t)(c0 + j), thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
+    return;
+  }
   if (act[0] && act[1] && act[2] && act[3]) {
     reinterpret_cast<float4*>(a.nws)[m] = make_float4(nws[0], nws[1], nws[2], nws[3]);
     reinterpret_cast<float4*>(a.nwd)[m] = make_float4(nwd[0], nwd[1], nwd[2], nwd[3]);
@@ -1274,6 +1333,20 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
     for (int j = 0; j < 4; ++j)
       if (act[j]) { a.nws[c0 + j] = nws[j]; a.nwd[c0 + j] = nwd[j]; }
   }
+}
+
+// K4c final: thresholds, scaling and state update (G:235-266) for every coastal-zone cell of the
+// compacted list, from n_thc (thc[], window kernel) and n_ws / n_wd (scratch planes, scan kernel).
+// An ordinary (fully stream-ordered) launch: it must see both the scan's and the window kernel's
+// results, and the window kernel -- a programmatic dependent of the scan that never waits for it --
+// may finish before the scan does.
+__global__ void __launch_bounds__(256) k_final(const TrigArgs a, const int* __restrict__ idx, int n_active)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_active) return;
+  const int c = idx[i];
+  trigger_point<SBD_VARIANT_GENERIC>(a, (size_t)c, (size_t)a.g.nx * a.g.ny, __ldcg(a.thc + c), __ldcg(a.nws + c),
+                                     __ldcg(a.nwd + c), 0.0f);
 }
 
 // flag functor for the compaction of quads with at least one coastal-zone cell
@@ -1329,6 +1402,7 @@ struct sbd_plan {
   float* d_nws = nullptr;     // scratch: wind speed at the selected level (scan -> window kernel)
   float* d_nwd = nullptr;     // scratch: wind direction at the selected level
   bool scan_done = false;     // sbd_plan_step_scan has been issued for the current step
+  int last_order = 0;         // kernel order used by the last generic step (see TrigArgs::order)
   const float *cur_p = nullptr, *cur_u = nullptr, *cur_v = nullptr;
   // optional per-kernel CUDA-event timing of the step (bench.py roofline leg)
   bool timing = false;
@@ -1488,14 +1562,38 @@ int dist_dev(cudaStream_t st, const float* d_coast, int coast_ld, int coast_off,
 // generic step, stage 1: level scan over p (+ wind at the selected level) into the scratch planes.
 // Needs p,u,v only -- neither theta nor its halos -- so a multi-GPU caller runs its halo exchange
 // beside it.
-int launch_scan(sbd_plan* p, TrigArgs& a)
+bool scan_vec_ok(const sbd_plan* p, const TrigArgs& a)
+{
+  return p->n_quads > 0 && a.prm.level_scan == 0 && (((uintptr_t)a.p) & 15) == 0 &&
+         (((uintptr_t)a.u) & 15) == 0 && (((uintptr_t)a.v) & 15) == 0;
+}
+
+template <int G, int QNT>
+int launch_scan_quad(sbd_plan* p, const TrigArgs& a, int qsmem, bool pdl)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(p->n_quads, QNT));
+  cfg.blockDim = dim3(QNT);
+  cfg.dynamicSmemBytes = qsmem;
+  cfg.stream = p->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const int* quads = p->d_quads;
+  int nq = p->n_quads;
+  CK(cudaLaunchKernelEx(&cfg, k_scan_quad<G, QNT>, a, quads, nq));
+  return SBD_OK;
+}
+
+int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false)
 {
   a.nws = p->d_nws;
   a.nwd = p->d_nwd;
-  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+  if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
   if (p->n_coastal > 0) {
-    const bool vec = p->n_quads > 0 && a.prm.level_scan == 0 && (((uintptr_t)a.p) & 15) == 0 &&
-                     (((uintptr_t)a.u) & 15) == 0 && (((uintptr_t)a.v) & 15) == 0;
+    const bool vec = scan_vec_ok(p, a);
     if (vec) {
       constexpr int QNT = 128;
       static int G = 0;
@@ -1524,23 +1622,24 @@ int launch_scan(sbd_plan* p, TrigArgs& a)
           CK(cudaFuncSetAttribute(k_scan_quad<14, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
         }
       }
-      const int nb = cdiv(p->n_quads, QNT);
-      if (G == 5) k_scan_quad<5, QNT><<<nb, QNT, qsmem, p->stream>>>(a, p->d_quads, p->n_quads);
-      else if (G == 7) k_scan_quad<7, QNT><<<nb, QNT, qsmem, p->stream>>>(a, p->d_quads, p->n_quads);
-      else if (G == 10) k_scan_quad<10, QNT><<<nb, QNT, qsmem, p->stream>>>(a, p->d_quads, p->n_quads);
-      else k_scan_quad<14, QNT><<<nb, QNT, qsmem, p->stream>>>(a, p->d_quads, p->n_quads);
+      const bool use_pdl = pdl && !p->timing;
+      int rc;
+      if (G == 5) rc = launch_scan_quad<5, QNT>(p, a, qsmem, use_pdl);
+      else if (G == 7) rc = launch_scan_quad<7, QNT>(p, a, qsmem, use_pdl);
+      else if (G == 10) rc = launch_scan_quad<10, QNT>(p, a, qsmem, use_pdl);
+      else rc = launch_scan_quad<14, QNT>(p, a, qsmem, use_pdl);
+      if (rc) return rc;
       LAUNCHED();
     } else {
       k_scan_scalar<14><<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
     }
   }
-  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+  if (p->timing) CK(cudaEventRecord(p->ev[3], p->stream));
   CK(cudaGetLastError());
   return SBD_OK;
 }
 
-// window kernel (+ thresholds).  Generic: launched as the programmatic dependent of the scan kernel
-// that precedes it in the stream.
+// one tile shape of the window kernel (see launch_trigger)
 template <int VARIANT, int TX, int TY, int NT, int RMAX>
 int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
 {
@@ -1553,13 +1652,16 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
   dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
   a.nws = p->d_nws;
   a.nwd = p->d_nwd;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SBD_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   if (!GEN) {
     if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
     kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();
-    if (p->timing) { CK(cudaEventRecord(p->ev[1], p->stream)); CK(cudaEventRecord(p->ev[2], p->stream)); }
+    if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
     CK(cudaGetLastError());
     return SBD_OK;
   }
+  // generic.  order 0: this kernel is the programmatic dependent of the scan that precedes it and
+  // k_final follows; order 1: ordinary launch, the scan (+thresholds) follows as its dependent.
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(NT);
@@ -1567,11 +1669,19 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = p->timing ? 0 : 1;  // timed runs: kernels in isolation
+  at[0].val.programmaticStreamSerializationAllowed = (a.order == 0 && !p->timing) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
   CK(cudaLaunchKernelEx(&cfg, kern, (const TrigArgs)a)); LAUNCHED();
-  if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
+  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+  if (a.order == 0) {
+    if (p->timing) CK(cudaEventRecord(p->ev[4], p->stream));
+    if (p->n_coastal > 0) {
+      k_final<<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
+    }
+    if (p->timing) CK(cudaEventRecord(p->ev[5], p->stream));
+  }
   CK(cudaGetLastError());
   return SBD_OK;
 }
@@ -1583,7 +1693,18 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
 template <int VARIANT>
 int launch_trigger(sbd_plan* p, TrigArgs& a)
 {
-  if (a.R <= 16) return launch_trigger_cfg<VARIANT, 64, 16, 256, 16>(p, a);
+  if (a.R <= 16) {
+    static int tile = -1;
+    if (tile < 0) { const char* e = getenv("SBD_TILE"); tile = e ? atoi(e) : 0; }
+    switch (tile) {
+      case 1: return launch_trigger_cfg<VARIANT, 64, 8, 256, 16>(p, a);
+      case 2: return launch_trigger_cfg<VARIANT, 64, 8, 128, 16>(p, a);
+      case 3: return launch_trigger_cfg<VARIANT, 32, 16, 128, 16>(p, a);
+      case 4: return launch_trigger_cfg<VARIANT, 64, 16, 512, 16>(p, a);
+      case 5: return launch_trigger_cfg<VARIANT, 64, 32, 512, 16>(p, a);
+      default: return launch_trigger_cfg<VARIANT, 64, 16, 256, 16>(p, a);
+    }
+  }
   return launch_trigger_cfg<VARIANT, 128, 64, 1024, 56>(p, a);
 }
 
@@ -1740,11 +1861,10 @@ int sbd_plan_last_timing(sbd_plan* p, float* ms3)
   if (!p || !ms3 || !p->ev[0]) return fail(SBD_EINVAL, "timing was not enabled");
   ms3[0] = ms3[1] = ms3[2] = 0.0f;
   CK(cudaStreamSynchronize(p->stream));
+  CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));              // window kernel
   if (p->variant == SBD_VARIANT_GENERIC) {
-    CK(cudaEventElapsedTime(&ms3[1], p->ev[0], p->ev[1]));  // level-scan kernel
-    CK(cudaEventElapsedTime(&ms3[0], p->ev[1], p->ev[2]));  // window + threshold kernel
-  } else {
-    CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));
+    CK(cudaEventElapsedTime(&ms3[1], p->ev[2], p->ev[3]));            // level-scan kernel
+    if (p->last_order == 0) CK(cudaEventElapsedTime(&ms3[2], p->ev[4], p->ev[5]));  // threshold kernel
   }
   return SBD_OK;
 }
@@ -1869,6 +1989,7 @@ int sbd_plan_step_scan(sbd_plan* p, const float* pp, const float* u, const float
   a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny;
   a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
   p->cur_p = a.p; p->cur_u = a.u; p->cur_v = a.v;
+  a.order = 0; p->last_order = 0;
   if ((rc = launch_scan(p, a))) return rc;
   p->scan_done = true;
   return SBD_OK;
@@ -1898,6 +2019,7 @@ int sbd_plan_step_finish(sbd_plan* p, float timestep, int step, const float* the
   a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
   a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
   p->scan_done = false;
+  a.order = 0;
   if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
   return flush_out(p, pend, any_host);
 }
@@ -1905,9 +2027,49 @@ int sbd_plan_step_finish(sbd_plan* p, float timestep, int step, const float* the
 int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const float* u, const float* v,
                   const float* theta, float* ws, float* wd, float* thc, float* sb, uint8_t* flags)
 {
-  int rc = sbd_plan_step_scan(p, pp, u, v);
-  if (rc) return rc;
-  return sbd_plan_step_finish(p, timestep, step, theta, ws, wd, thc, sb, flags);
+  if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
+  if (!p->have_static) return fail(SBD_EINVAL, "sbd_plan_set_static has not been called");
+  if (!pp || !u || !v || !theta || !ws || !wd || !thc || !sb) return fail(SBD_EINVAL, "NULL argument");
+  static int order_env = -1;
+  if (order_env < 0) { const char* e = getenv("SBD_ORDER"); order_env = e ? atoi(e) : 1; }
+  if (order_env == 0) {
+    int rc = sbd_plan_step_scan(p, pp, u, v);
+    if (rc) return rc;
+    return sbd_plan_step_finish(p, timestep, step, theta, ws, wd, thc, sb, flags);
+  }
+  // single call, nothing to overlap with on the host side: window kernel first, the level scan as
+  // its programmatic dependent with the thresholds in its epilogue (two launches, no scratch pass)
+  const size_t n2 = (size_t)p->nx * p->ny, n3 = n2 * p->nz, nh = plane_elems(p);
+  p->stage_used = 0;
+  std::vector<OutView> pend;
+  TrigArgs a{};
+  int rc;
+  const bool any_host = !is_device_ptr(pp) || !is_device_ptr(theta) || !is_device_ptr(u) || !is_device_ptr(v);
+  if ((rc = in_view(p, pp, n3, &a.p, true))) return rc;
+  if ((rc = in_view(p, u, n3, &a.u, true))) return rc;
+  if ((rc = in_view(p, v, n3, &a.v, true))) return rc;
+  if ((rc = in_view(p, theta, nh, &a.theta))) return rc;
+  void* d;
+  if ((rc = out_view(p, ws, n2 * 4, true, &d, pend))) return rc; a.ws = (float*)d;
+  if ((rc = out_view(p, wd, n2 * 4, true, &d, pend))) return rc; a.wd = (float*)d;
+  if ((rc = out_view(p, thc, n2 * 4, true, &d, pend))) return rc; a.thc = (float*)d;
+  if ((rc = out_view(p, sb, n2 * 4, false, &d, pend))) return rc; a.sb = (float*)d;
+  if ((rc = out_view(p, flags, n2, false, &d, pend))) return rc; a.flags = (uint8_t*)d;
+  a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny;
+  a.first_step = step < 2 ? 1 : 0;
+  a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
+  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  if (!scan_vec_ok(p, a) || p->n_coastal == 0) {
+    // scalar scan / no coastal cells: scan -> window -> final, in order
+    a.order = 0; p->last_order = 0;
+    if ((rc = launch_scan(p, a))) return rc;
+    if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
+    return flush_out(p, pend, any_host);
+  }
+  a.order = 1; p->last_order = 1;
+  if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
+  if ((rc = launch_scan(p, a, true))) return rc;
+  return flush_out(p, pend, any_host);
 }
 
 int sbd_plan_step_py(sbd_plan* p, int step, float timestep_min, const float* pp, const float* u,

@@ -229,6 +229,9 @@ def main():
     torch.cuda.synchronize()
     torch.cuda.set_stream(stream)
     plan.set_stream(stream.cuda_stream)
+    # swap_bounds of the per-step field theta is folded into the kernels' reads (E-W periodic wrap,
+    # domain-edge rows); between ranks the N-S halo rows still travel by NCCL every step
+    plan.set_halo_mode(ex.halo_mode())
     t_static0 = time.perf_counter()
     stats = ex.global_sigma_stats(sh) if world > 1 else None
     plan.set_static(mk, zh, sh, stats=stats)
@@ -242,12 +245,11 @@ def main():
     ev_prev = [None]
 
     def one_step(k):
-        """One timestep.  theta's halo is refreshed every step (it is a per-step input): E-W periodic
-        fill on the GPU, N-S rows from the neighbour ranks by NCCL send/recv.  With several ranks
-        the exchange runs on its own stream beside the level scan, which needs no halos."""
+        """One timestep.  theta's halo is a per-step input: the E-W periodic wrap and the domain-edge
+        rows are read in place by the kernels (plan halo mode), N-S rows owned by neighbour ranks
+        arrive by NCCL send/recv on a separate stream beside the level scan, which needs no halos."""
         th, p, u, v = dsteps[k % NSETS]
         if world == 1:
-            ex.swap_bounds_step(th)
             plan.step(cfg.timestep, k + 2, p, u, v, th, *state, flags=flags)
             return
         plan.step_scan(p, u, v)
@@ -331,7 +333,6 @@ def main():
         t0 = time.perf_counter()
         for i in range(ne):
             th_h, p, u, v = hsteps[i % 2]
-            generic.swap_bounds(th_h, h, ew_only=(world > 1))
             plan.step(cfg.timestep, i + 4, p, u, v, th_h, *hstate, flags=hflags)  # blocking: outputs are on the host
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -339,10 +340,16 @@ def main():
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        h2d = 4 * (3 * n_cells * nz + 2 * (nx + 2 * h) * (ny + 2 * h) + 3 * n_cells)
-        d2h = 4 * (4 * n_cells) + n_cells + 4 * (nx + 2 * h) * (ny + 2 * h)
+        # p,u,v sit in pinned host memory and are gathered in place by the level scan (zero-copy):
+        # 16 B per quad and level of p plus one level of u and v cross PCIe; theta and the three
+        # state planes are staged by cudaMemcpyAsync, the four result planes + flags come back
+        nq = info["n_quads"]
+        h2d = 16 * nq * (nz + 2) + 4 * ((nx + 2 * h) * (ny + 2 * h) + 3 * n_cells)
+        d2h = 4 * (4 * n_cells) + n_cells
         e2e = {"value": world * n_cells * ne / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": ne, "ms_per_step": 1e3 * dt / ne}
+               "d2h_bytes_per_step": d2h, "steps": ne, "ms_per_step": 1e3 * dt / ne,
+               "api": "Plan.step with numpy arrays in pinned host memory (blocking call)",
+               "host_input_bytes_per_step": 4 * (3 * n_cells * nz + (nx + 2 * h) * (ny + 2 * h) + 3 * n_cells)}
 
     if rank != 0:
         if world > 1:

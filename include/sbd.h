@@ -153,6 +153,13 @@ int sbd_plan_use_own_stream(sbd_plan* plan);
 void* sbd_plan_get_stream(sbd_plan* plan);
 int sbd_plan_sync(sbd_plan* plan);
 
+/* Generic variant: fold the single-domain swap_bounds of the per-step field theta (and of the
+ * static planes) into the kernels' reads instead of reading halo memory.  mode is a bit mask:
+ * 1 = east-west periodic, 2 = north edge row replicated, 4 = south edge row replicated; 0 (default)
+ * = read the halos the caller filled (reference semantics).  A row-block rank sets 1 plus the
+ * bit of each side that is a domain edge and exchanges only the other side's rows.  Call before
+ * sbd_plan_set_static. */
+int sbd_plan_set_halo_mode(sbd_plan* plan, int mode);
 /* Static fields: mask = signed coast distance, z, sigma (generic: halo'd; python: nlons x nlats).
  * Computes the sigmoid statistics (sequential-order exact), the sea-level correction plane
  * gmma*z*sigmoid(sigma), the land/sea sign plane and every cell's final search radius nn.
@@ -163,6 +170,9 @@ int sbd_plan_set_static(sbd_plan* plan, const float* mask, const float* z, const
 /* Largest search radius found by set_static and the sigmoid statistics (mean, 2/sigma, r, var). */
 int sbd_plan_info(sbd_plan* plan, int* nn_max, int* n_coastal, float* stats4);
 
+/* Number of aligned 4-cell groups with at least one coastal-zone cell (the units the level scan
+ * streams; 16 bytes per group and level).  -1 before sbd_plan_set_static. */
+int sbd_plan_n_quads(sbd_plan* plan);
 /* One timestep, generic variant (G:170-269 after G:166-167). */
 int sbd_plan_step(sbd_plan* plan, float timestep, int timestep_number, const float* p, const float* u,
                   const float* v, const float* theta, float* windspeed, float* winddir, float* thc,

@@ -78,6 +78,7 @@ struct Geo {
   int h;       // halo (generic) / 0 (python)
   int ldx;     // row pitch of the 2-D neighbour-read planes
   int ldy;     // rows of those planes
+  int vh;      // generic: "virtual halo" bits (sbd_plan_set_halo_mode), 0 = read the halo memory
 };
 
 // GENERIC: raw halo'd index (G:200-201).  PYTHON: ki = clamp(ii), kj = max(1, modulo(jj, nlons))
@@ -87,6 +88,11 @@ template <int VARIANT>
 __device__ __forceinline__ int nbr_index(const Geo& g, int gx, int gy)
 {
   if (VARIANT == SBD_VARIANT_GENERIC) {
+    // virtual halo: the single-domain swap_bounds (east-west periodic, north-south edge rows)
+    // folded into the read, so the halo memory of that side is never touched
+    if (g.vh & 1) gx = (gx < 0) ? gx + g.nx : ((gx >= g.nx) ? gx - g.nx : gx);
+    if ((g.vh & 2) && gy < 0) gy = 0;
+    if ((g.vh & 4) && gy >= g.ny) gy = g.ny - 1;
     int x = min(max(gx + g.h, 0), g.ldx - 1);
     int y = min(max(gy + g.h, 0), g.ldy - 1);
     return y * g.ldx + x;
@@ -220,7 +226,7 @@ __global__ void k_edges_py(const float* __restrict__ lsm, const float* __restric
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= nx) return;
-  Geo g{nx, ny, 0, nx, ny};
+  Geo g{nx, ny, 0, nx, ny, 0};
   int m[3][3];
 #pragma unroll
   for (int i = -1; i <= 1; ++i)
@@ -1807,7 +1813,7 @@ int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, 
   sbd_plan* p = new sbd_plan();
   p->variant = variant; p->nx = nx; p->ny = ny; p->nz = nz;
   p->h = (variant == SBD_VARIANT_GENERIC) ? h : 0;
-  p->g = Geo{nx, ny, p->h, nx + 2 * p->h, ny + 2 * p->h};
+  p->g = Geo{nx, ny, p->h, nx + 2 * p->h, ny + 2 * p->h, 0};
   if (prm) p->prm = *prm; else sbd_default_params(&p->prm, variant);
   cudaError_t e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete p; snprintf(g_err, sizeof g_err, "cudaStreamCreate: %s", cudaGetErrorString(e)); return SBD_ECUDA; }
@@ -1846,6 +1852,14 @@ int sbd_plan_set_stream(sbd_plan* p, void* stream)
 {
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
   p->stream = (cudaStream_t)stream;  // NULL = the legacy default stream (torch's default stream)
+  return SBD_OK;
+}
+int sbd_plan_set_halo_mode(sbd_plan* p, int mode)
+{
+  if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
+  if (mode < 0 || mode > 7) return fail(SBD_EINVAL, "halo mode is a 3-bit mask");
+  if ((mode & 1) && p->h > p->nx) return fail(SBD_EINVAL, "periodic virtual halo needs halo <= nx");
+  p->g.vh = mode;
   return SBD_OK;
 }
 int sbd_plan_set_timing(sbd_plan* p, int on)
@@ -1968,6 +1982,8 @@ int sbd_plan_info(sbd_plan* p, int* nn_max, int* n_coastal, float* stats4)
   if (stats4) memcpy(stats4, p->stats, sizeof p->stats);
   return SBD_OK;
 }
+
+int sbd_plan_n_quads(sbd_plan* p) { return (p && p->have_static) ? p->n_quads : -1; }
 
 static int six_hourly_flag(int step, float timestep_s, float target_time)
 {

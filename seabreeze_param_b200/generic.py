@@ -133,6 +133,10 @@ class Plan:
     def stream(self):
         return self.lib.sbd_plan_get_stream(self._h)
 
+    def set_halo_mode(self, mode):
+        """Fold swap_bounds into the kernels' reads: bit0 E-W periodic, bit1 north edge, bit2 south edge."""
+        _capi.check(self.lib.sbd_plan_set_halo_mode(self._h, int(mode)), "plan_set_halo_mode")
+
     def use_own_stream(self):
         _capi.check(self.lib.sbd_plan_use_own_stream(self._h), "plan_use_own_stream")
 
@@ -159,7 +163,7 @@ class Plan:
         nn, nc = C.c_int(), C.c_int()
         st = np.zeros(4, dtype=np.float32)
         _capi.check(self.lib.sbd_plan_info(self._h, C.byref(nn), C.byref(nc), _capi.ptr(st)), "plan_info")
-        return {"nn_max": nn.value, "n_coastal": nc.value, "mean": float(st[0]), "std2inv": float(st[1]),
+        return {"nn_max": nn.value, "n_coastal": nc.value, "n_quads": int(self.lib.sbd_plan_n_quads(self._h)), "mean": float(st[0]), "std2inv": float(st[1]),
                 "r": float(st[2]), "var": float(st[3])}
 
     def step(self, timestep, timestep_number, p, u, v, theta, windspeed, winddir, thc, sb_con, flags=None):

@@ -52,9 +52,17 @@ class RowBlockHalo:
         if self.ns_mask & 2:
             field[ny + h:, :] = field[ny + h - 1:ny + h, :]
 
-    def swap_bounds(self, field):
+    def halo_mode(self):
+        """Bit mask for Plan.set_halo_mode: E-W periodic wrap and the replicated domain-edge rows are
+        folded into the kernels' reads; only rows owned by a neighbour rank are exchanged."""
+        return 1 | (self.ns_mask << 1)
+
+    def swap_bounds(self, field, local_fill=True):
+        """local_fill=False: the plan runs with halo_mode() (virtual halos), so only the NCCL
+        exchange of neighbour-owned rows is left to do."""
         h, ny = self.h, self.ny
-        self._local_fill(field)
+        if local_fill:
+            self._local_fill(field)
         if self.world > 1:
             import torch.distributed as dist
             ops = []
@@ -68,7 +76,9 @@ class RowBlockHalo:
                 w.wait()
         return field
 
-    swap_bounds_step = swap_bounds
+    def swap_bounds_step(self, field):
+        """Per-timestep halo refresh of theta for a plan in halo_mode(): exchange only."""
+        return self.swap_bounds(field, local_fill=False)
 
     # -- global sequential statistics of sigma over all ranks' interiors (rank-ordered carry) --
     def global_sigma_stats(self, sigma_h):

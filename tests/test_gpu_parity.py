@@ -206,6 +206,34 @@ def test_generic_seabreeze_diag_steps(oracle, name, level_scan):
     plan.close()
 
 
+def test_generic_virtual_halo(oracle):
+    """Plan halo mode 7: swap_bounds folded into the kernels' reads -- theta arrives with garbage in
+    its halo and the result equals the run with explicitly filled halos."""
+    cfg = synth.CONFIGS["t_gen"]
+    case = generic_case(cfg, oracle)
+    ny, nx, h = cfg.ny, cfg.nx, cfg.h
+    plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, h)
+    plan.set_halo_mode(7)
+    def junk(a):
+        b = np.full_like(a, 1.0e30)
+        b[h:h + ny, h:h + nx] = a[h:h + ny, h:h + nx]
+        return b
+
+    plan.set_static(junk(case["mask_h"]), junk(case["z_h"]), junk(case["sigma_h"]))
+    so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    sp = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    for step in (1, 2, 15):
+        theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
+        fo = oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"],
+                                   case["sigma_h"], *so, h)
+        fp = np.zeros((ny, nx), np.uint8)
+        plan.step(cfg.timestep, step, p, u, v, junk(theta_h), *sp, flags=fp)
+        for a, b, nm in zip(so, sp, ("windspeed", "winddir", "thc", "sb_con")):
+            assert_bits_equal(a, b, "%s step %d" % (nm, step))
+        assert np.array_equal(fo, fp)
+    plan.close()
+
+
 def test_generic_device_pointers_torch(oracle):
     """Same step with every array resident on the GPU (torch tensors): the path bench.py times."""
     import torch

@@ -217,9 +217,22 @@ def main():
     mk = ex.swap_bounds(haloed(cdist))
     zh = ex.swap_bounds(haloed(t(z)))
     sh = ex.swap_bounds(haloed(t(sig)))
+    # With several ranks theta lives in symmetric (peer-mapped) memory: the window kernel reads the
+    # halo rows owned by a neighbour rank straight from that rank's plane over NVLink.
+    # BENCH_HALO=nccl selects the send/recv exchange instead.
+    use_peer = world > 1 and os.environ.get("BENCH_HALO", "peer") == "peer"
+    peer = halo.PeerHalo(NSETS, ny, nx, h, rank, world, dev) if use_peer else None
     dsteps = []
-    for theta, p, u, v in steps:
-        dsteps.append((haloed(t(theta)), t(p), t(u), t(v)))
+    for i, (theta, p, u, v) in enumerate(steps):
+        if peer is not None:
+            th = peer.plane(i)
+            th[h:h + ny, h:h + nx] = t(theta)
+        else:
+            th = haloed(t(theta))
+        dsteps.append((th, t(p), t(u), t(v)))
+    if peer is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
     state = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(4)]
     flags = torch.zeros((ny, nx), dtype=torch.uint8, device=dev)
 
@@ -252,11 +265,20 @@ def main():
         if world == 1:
             plan.step(cfg.timestep, k + 2, p, u, v, th, *state, flags=flags)
             return
+        if peer is not None:
+            # symmetric-memory path: one device-side barrier ("every rank's theta of this step is in
+            # place, nobody still reads the previous one"), then the ordinary two-kernel step whose
+            # window kernel reads the neighbours' rows over NVLink -- no copy, no extra stream
+            peer.barrier()
+            plan.set_peer_theta(*peer.peers(k % NSETS))
+            plan.step(cfg.timestep, k + 2, p, u, v, th, *state, flags=flags)
+            return
+        # NCCL path: the exchange runs on its own stream beside the level scan
         plan.step_scan(p, u, v)
         if ev_prev[0] is not None:
             comm.wait_event(ev_prev[0])
         with torch.cuda.stream(comm):
-            ex.swap_bounds_step(th)
+            ex.swap_bounds_step(th)  # NCCL send/recv of the N-S halo rows
             ev_h = comm.record_event()
         stream.wait_event(ev_h)
         plan.step_finish(cfg.timestep, k + 2, th, *state, flags=flags)
@@ -409,7 +431,9 @@ def main():
                    "api": "plan step (static fields processed once per plan: %.1f ms, SURVEY 8d)" % static_ms,
                    "l2": "rotating %d input sets of p,u,v (%.0f MB each) > 126 MB L2; no flush kernel in the timed region"
                          % (NSETS, 3 * 4 * n_cells * nz / 1e6),
-                   "parallelism": "row-block x%d, theta halo via NCCL send/recv" % world if world > 1 else "single GPU"},
+                   "parallelism": ("row-block x%d, theta halo rows %s" % (
+                       world, "read from the neighbours' planes over NVLink (symmetric memory) + per-step device barrier"
+                       if use_peer else "via NCCL send/recv")) if world > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "static_setup_ms": static_ms,
     }

@@ -160,6 +160,12 @@ int sbd_plan_sync(sbd_plan* plan);
  * bit of each side that is a domain edge and exchanges only the other side's rows.  Call before
  * sbd_plan_set_static. */
 int sbd_plan_set_halo_mode(sbd_plan* plan, int mode);
+/* Multi-GPU row blocks without a per-step copy: device pointers to the halo'd theta planes of the
+ * northern / southern neighbour rank, mapped into this process (CUDA peer or symmetric memory over
+ * NVLink).  The window kernel then reads the halo rows it needs straight from the neighbours'
+ * interior rows; NULL = that side's halo comes from this plane (or the halo mode).  ny_up = interior
+ * rows of the northern neighbour.  The pointers stay in force until changed. */
+int sbd_plan_set_peer_theta(sbd_plan* plan, const float* theta_up, int ny_up, const float* theta_dn);
 /* Static fields: mask = signed coast distance, z, sigma (generic: halo'd; python: nlons x nlats).
  * Computes the sigmoid statistics (sequential-order exact), the sea-level correction plane
  * gmma*z*sigmoid(sigma), the land/sea sign plane and every cell's final search radius nn.

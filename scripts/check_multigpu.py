@@ -30,6 +30,12 @@ plan = generic.Plan(SBD_VARIANT_GENERIC, nx, nyl, nz, h)
 plan.set_static(mk, zh, sh, stats=stats)
 st = [torch.zeros((nyl, nx), dtype=torch.float32, device=dev) for _ in range(4)]
 fl = torch.zeros((nyl, nx), dtype=torch.uint8, device=dev)
+# second plan: no exchange at all -- halo rows of theta are read from the neighbours' planes (peer memory)
+peer = halo.PeerHalo(1, nyl, nx, h, rank, world, dev)
+plan_p = generic.Plan(SBD_VARIANT_GENERIC, nx, nyl, nz, h)
+plan_p.set_halo_mode(ex.halo_mode())
+plan_p.set_static(mk, zh, sh, stats=stats)
+st_p = [torch.zeros((nyl, nx), dtype=torch.float32, device=dev) for _ in range(4)]
 ok = True
 if rank == 0:
     ex1 = halo.RowBlockHalo(nx, ny, h, 0, 1, dev)
@@ -45,6 +51,20 @@ for step in (1, 2, 15):
     th = ex.swap_bounds(haloed(t(theta[r0:r1]), nyl))
     plan.step(cfg.timestep, step, t(p[:, r0:r1]), t(u[:, r0:r1]), t(v[:, r0:r1]), th, *st, flags=fl)
     plan.sync()
+    pl = peer.plane(0)
+    pl.fill_(7.0e30)                               # halos hold junk: they must not be read
+    pl[h:h + nyl, h:h + nx] = t(theta[r0:r1])
+    torch.cuda.synchronize(); peer.barrier(); torch.cuda.synchronize()
+    plan_p.set_peer_theta(*peer.peers(0))
+    plan_p.step(cfg.timestep, step, t(p[:, r0:r1]), t(u[:, r0:r1]), t(v[:, r0:r1]), pl, *st_p)
+    plan_p.sync()
+    torch.cuda.synchronize(); peer.barrier(); torch.cuda.synchronize()
+    for s_a, s_b, nm in zip(st, st_p, ("ws", "wd", "thc", "sb")):
+        a_, b_ = s_a.cpu().numpy(), s_b.cpu().numpy()
+        same = (a_.view(np.uint32) == b_.view(np.uint32)) | (np.isnan(a_) & np.isnan(b_))
+        if not same.all():
+            print("rank", rank, "step", step, nm, "PEER path DIFFERENT (%d cells)" % (~same).sum())
+            ok = False
     outs = [torch.empty((world, nyl, nx), dtype=torch.float32, device=dev) for _ in range(4)]
     for o, s_ in zip(outs, st):
         dist.all_gather_into_tensor(o, s_.contiguous())
@@ -57,7 +77,9 @@ for step in (1, 2, 15):
             same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
             print("step", step, nm, "identical" if same.all() else "DIFFERENT (%d cells)" % (~same).sum())
             ok &= bool(same.all())
+okt = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(okt, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("MULTIGPU_CHECK", "PASS" if ok else "FAIL", "world", world)
+    print("MULTIGPU_CHECK", "PASS" if int(okt.item()) else "FAIL", "world", world, "(NCCL exchange and peer-memory halo reads vs 1 rank)")
 dist.barrier()
 dist.destroy_process_group()

@@ -21,7 +21,7 @@ SYMBOLS = [
     "sbd_get_threads",
     "sbd_plan_create", "sbd_plan_destroy", "sbd_plan_set_stream", "sbd_plan_use_own_stream", "sbd_plan_get_stream",
     "sbd_plan_sync", "sbd_plan_set_static", "sbd_plan_info", "sbd_plan_n_quads", "sbd_plan_step", "sbd_plan_step_scan", "sbd_plan_step_finish", "sbd_plan_step_py",
-    "sbd_launch_count", "sbd_stats_chain_f32", "sbd_plan_set_timing", "sbd_plan_last_timing", "sbd_plan_set_halo_mode",
+    "sbd_launch_count", "sbd_stats_chain_f32", "sbd_plan_set_timing", "sbd_plan_last_timing", "sbd_plan_set_halo_mode", "sbd_plan_set_peer_theta",
 ]
 
 
@@ -93,6 +93,7 @@ def load():
     lib.sbd_plan_step_finish.argtypes = [vp, f, i, fp, fp, fp, fp, fp, vp]
     lib.sbd_plan_step_py.argtypes = [vp, i, f, fp, fp, fp, fp, fp, fp, fp, vp]
     lib.sbd_plan_set_halo_mode.argtypes = [vp, i]
+    lib.sbd_plan_set_peer_theta.argtypes = [vp, fp, i, fp]
     lib.sbd_plan_set_timing.argtypes = [vp, i]
     lib.sbd_plan_last_timing.argtypes = [vp, fp]
     lib.sbd_stats_chain_f32.argtypes = [fp, i, i, i, i, i, fp]

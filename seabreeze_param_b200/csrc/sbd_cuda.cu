@@ -809,9 +809,32 @@ struct TrigArgs {
   // generic: wind speed / direction at the selected level, written by the level-scan kernel and
   // consumed by the window kernel's threshold stage (plan-owned scratch planes, nx x ny)
   float* nws; float* nwd;
+  // multi-GPU row blocks: theta planes of the neighbour ranks, mapped into this process over
+  // NVLink (peer / symmetric memory).  Halo rows north (south) of the block are read from them in
+  // place instead of from a halo that somebody would have to fill first.
+  const float* theta_up; const float* theta_dn;
+  int ny_up;  // interior rows of the northern neighbour's block
   int order;  // 0: scan -> window -> final (multi-GPU friendly); 1: window -> scan(+thresholds)
   int dbg;  // profiling experiments only (SBD_DBG): bit0 skip window sums, bit1 skip thresholds, bit2 skip staging
 };
+
+// theta at interior-relative (gx, gy): the local plane, or -- for rows that belong to a neighbouring
+// rank whose plane is peer-mapped -- that rank's interior rows, read over NVLink.
+template <int VARIANT>
+__device__ __forceinline__ float load_theta(const TrigArgs& a, int gx, int gy, int sidx_local)
+{
+  if (VARIANT == SBD_VARIANT_GENERIC) {
+    const bool up = (gy < 0) && a.theta_up, dn = (gy >= a.g.ny) && a.theta_dn;
+    if (up || dn) {
+      if (a.g.vh & 1) gx = (gx < 0) ? gx + a.g.nx : ((gx >= a.g.nx) ? gx - a.g.nx : gx);
+      const int x = min(max(gx + a.g.h, 0), a.g.ldx - 1);
+      const int row = up ? (a.ny_up + gy) : (gy - a.g.ny);
+      const float* base = up ? a.theta_up : a.theta_dn;
+      return base[(size_t)(row + a.g.h) * a.g.ldx + x];
+    }
+  }
+  return a.theta[sidx_local];
+}
 
 template <int VARIANT>
 __device__ __forceinline__ void window_sums_global(const TrigArgs& a, int gx, int gy, int nn, float& T_l,
@@ -820,7 +843,7 @@ __device__ __forceinline__ void window_sums_global(const TrigArgs& a, int gx, in
   for (int ii = gy - nn; ii <= gy + nn; ++ii)
     for (int jj = gx - nn; jj <= gx + nn; ++jj) {
       const int s = nbr_index<VARIANT>(a.g, jj, ii);
-      const float t = a.theta[s] - a.gzsm[s];
+      const float t = load_theta<VARIANT>(a, jj, ii, s) - a.gzsm[s];
       if (a.code[s] & 0x8000u) { T_l = T_l + t; ++c_l; }
       else { T_s = T_s + t; ++c_s; }
     }
@@ -984,7 +1007,7 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
         th[cch] = 0.0f; gz[cch] = 0.0f; cd[cch] = 0u;
         if (lx < W) {
           const int sidx = nbr_index<VARIANT>(a.g, x0 - R + lx, y0 - R + ly);
-          th[cch] = a.theta[sidx];
+          th[cch] = load_theta<VARIANT>(a, x0 - R + lx, y0 - R + ly, sidx);
           gz[cch] = a.gzsm[sidx];
           cd[cch] = a.code[sidx];
         }
@@ -1409,6 +1432,8 @@ struct sbd_plan {
   float* d_nwd = nullptr;     // scratch: wind direction at the selected level
   bool scan_done = false;     // sbd_plan_step_scan has been issued for the current step
   int last_order = 0;         // kernel order used by the last generic step (see TrigArgs::order)
+  const float *peer_up = nullptr, *peer_dn = nullptr;  // neighbour ranks' theta planes (peer-mapped)
+  int peer_ny_up = 0;
   const float *cur_p = nullptr, *cur_u = nullptr, *cur_v = nullptr;
   // optional per-kernel CUDA-event timing of the step (bench.py roofline leg)
   bool timing = false;
@@ -1862,6 +1887,13 @@ int sbd_plan_set_halo_mode(sbd_plan* p, int mode)
   p->g.vh = mode;
   return SBD_OK;
 }
+int sbd_plan_set_peer_theta(sbd_plan* p, const float* theta_up, int ny_up, const float* theta_dn)
+{
+  if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
+  if (theta_up && ny_up < p->h) return fail(SBD_EINVAL, "northern neighbour block is thinner than the halo");
+  p->peer_up = theta_up; p->peer_dn = theta_dn; p->peer_ny_up = ny_up;
+  return SBD_OK;
+}
 int sbd_plan_set_timing(sbd_plan* p, int on)
 {
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
@@ -2034,6 +2066,7 @@ int sbd_plan_step_finish(sbd_plan* p, float timestep, int step, const float* the
   a.first_step = step < 2 ? 1 : 0;
   a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
   a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  a.theta_up = p->peer_up; a.theta_dn = p->peer_dn; a.ny_up = p->peer_ny_up;
   p->scan_done = false;
   a.order = 0;
   if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
@@ -2075,6 +2108,7 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
   a.first_step = step < 2 ? 1 : 0;
   a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
   a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  a.theta_up = p->peer_up; a.theta_dn = p->peer_dn; a.ny_up = p->peer_ny_up;
   if (!scan_vec_ok(p, a) || p->n_coastal == 0) {
     // scalar scan / no coastal cells: scan -> window -> final, in order
     a.order = 0; p->last_order = 0;

@@ -137,6 +137,11 @@ class Plan:
         """Fold swap_bounds into the kernels' reads: bit0 E-W periodic, bit1 north edge, bit2 south edge."""
         _capi.check(self.lib.sbd_plan_set_halo_mode(self._h, int(mode)), "plan_set_halo_mode")
 
+    def set_peer_theta(self, theta_up, ny_up, theta_dn):
+        """Neighbour ranks' halo'd theta planes (peer-mapped tensors / addresses, or None)."""
+        _capi.check(self.lib.sbd_plan_set_peer_theta(self._h, _capi.ptr(theta_up), int(ny_up), _capi.ptr(theta_dn)),
+                    "plan_set_peer_theta")
+
     def use_own_stream(self):
         _capi.check(self.lib.sbd_plan_use_own_stream(self._h), "plan_use_own_stream")
 

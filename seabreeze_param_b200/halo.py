@@ -126,3 +126,37 @@ class RowBlockHalo:
         std = np.float32(np.float32(2.0) / np.sqrt(np.float32(var / n_glob)))
         r = np.float32(np.float32(c0[2] - c0[3]) / np.float32(4.0))
         return np.array([mean, std, r], dtype=np.float32)
+
+
+class PeerHalo:
+    """Per-step halo rows without a copy: every rank keeps its halo'd theta planes in symmetric
+    memory (torch.distributed._symmetric_memory: peer-mapped allocations over NVLink / NVSwitch),
+    and the window kernel of a neighbour reads the rows it needs straight from them
+    (Plan.set_peer_theta).  What is left per step is a device-side barrier over the symmetric
+    memory's signal pads ("my theta for this step is in place / I am done reading yours")."""
+
+    def __init__(self, nbuf, ny_local, nx, h, rank, world, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.ny, self.h = rank, world, ny_local, h
+        shape = (nbuf, ny_local + 2 * h, nx + 2 * h)
+        self.buf = symm.empty(shape, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.up = self.hdl.get_buffer(rank - 1, shape, torch.float32) if rank > 0 else None
+        self.dn = self.hdl.get_buffer(rank + 1, shape, torch.float32) if rank < world - 1 else None
+        plane_bytes = 4 * shape[1] * shape[2]
+        self._peers = [(self.up.data_ptr() + i * plane_bytes if self.up is not None else None, ny_local,
+                        self.dn.data_ptr() + i * plane_bytes if self.dn is not None else None) for i in range(nbuf)]
+
+    def plane(self, i):
+        return self.buf[i]
+
+    def peers(self, i):
+        """(address of the northern neighbour's plane i or None, its interior rows, address of the
+        southern neighbour's plane i or None) -- the arguments of Plan.set_peer_theta"""
+        return self._peers[i]
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)

@@ -221,7 +221,17 @@ def main():
     # halo rows owned by a neighbour rank straight from that rank's plane over NVLink.
     # BENCH_HALO=nccl selects the send/recv exchange instead.
     use_peer = world > 1 and os.environ.get("BENCH_HALO", "peer") == "peer"
-    peer = halo.PeerHalo(NSETS, ny, nx, h, rank, world, dev) if use_peer else None
+    peer = None
+    if use_peer:
+        try:
+            peer = halo.PeerHalo(NSETS, ny, nx, h, rank, world, dev)
+        except Exception as e:  # no symmetric memory on this box: fall back to NCCL send/recv
+            sys.stderr.write("bench: symmetric memory unavailable (%r), using NCCL halo exchange\n" % (e,))
+            use_peer = False
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer, use_peer = None, False
     dsteps = []
     for i, (theta, p, u, v) in enumerate(steps):
         if peer is not None:

@@ -815,7 +815,6 @@ struct TrigArgs {
   const float* theta_up; const float* theta_dn;
   int ny_up;  // interior rows of the northern neighbour's block
   int order;  // 0: scan -> window -> final (multi-GPU friendly); 1: window -> scan(+thresholds)
-  int dbg;  // profiling experiments only (SBD_DBG): bit0 skip window sums, bit1 skip thresholds, bit2 skip staging
 };
 
 // theta at interior-relative (gx, gy): the local plane, or -- for rows that belong to a neighbouring
@@ -957,7 +956,7 @@ __device__ __forceinline__ void window_fixed(const float* __restrict__ s_t0, con
 //            run in k_scan_quad / k_final.  Otherwise (python: one global level) the thresholds
 //            are applied here.
 template <int VARIANT, int TX, int TY, int NT, int RMAX, bool SPLIT>
-__global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
+__global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(const TrigArgs a)
 {
   constexpr int CPT = TX * TY / NT;  // cells per thread in phase 2
   constexpr int NB = 64;             // nn buckets: 1..NB-2 exact, NB-1 = "wider than the tile halo"
@@ -998,7 +997,7 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
   {
     constexpr int MAXC = (TX + 2 * RMAX + 31) / 32;  // R <= RMAX for this tile shape
     const int warp = tid >> 5, lane = tid & 31;
-    for (int ly = warp; ly < ((a.dbg & 4) ? 0 : Hh); ly += NT / 32) {
+    for (int ly = warp; ly < Hh; ly += NT / 32) {
       float th[MAXC], gz[MAXC];
       uint32_t cd[MAXC];
 #pragma unroll
@@ -1087,9 +1086,7 @@ __global__ void __launch_bounds__(NT) k_trigger(const TrigArgs a)
     int nn = bkt;
     float T_l = 0.0f, T_s = 0.0f;
     uint32_t c_l = 0, c_s = 0;
-    if (a.dbg & 1) {
-      T_l = 1.0f; T_s = 2.0f; c_l = 1; c_s = 1;
-    } else if (bkt != NB - 1) {
+    if (bkt != NB - 1) {
       const int lcx = R + lx, lcy = R + ly;
       switch (nn) {
         case 1: window_fixed<1>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
@@ -1683,7 +1680,6 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
   dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
   a.nws = p->d_nws;
   a.nwd = p->d_nwd;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SBD_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   if (!GEN) {
     if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
     kern<<<grid, NT, smem, p->stream>>>(a); LAUNCHED();

@@ -133,6 +133,20 @@ int sbd_py_diag_f32(int timestep_number, const float* p, const float* z, const f
                     float target_time, float maxdist, float timestep, int nps, int nlons, int nlats,
                     float* output, uint8_t* flags);
 
+/* The whole time loop of seabreezediag.diag() (python_wrapper/seabreezediag/__init__.py:219-245) in
+ * one call: for r = 0..nrec-1: dist_r = get_dist(get_edges(lsm, ci_r), lsm, lon, lat);
+ * output_r = diag(timestep_number0 + r, p, z, std, theta_r, v_r, u_r, dist_r, ws_{r-1}, wd_{r-1}, ...)
+ * with ws_r, wd_r = planes 3,4 of output_r (I:244) and ws_{-1}, wd_{-1} = ws0, wd0.
+ * theta (nlons,nlats,nrec); u,v (nlons,nlats,nps,nrec); ci (nlons,nlats,nrec) or NULL (no ice);
+ * output (nlons,nlats,4,nrec); flags optional (nlons,nlats,nrec).  Everything stays on the device
+ * between records; the coast distance is recomputed only when ci_r differs from ci_{r-1}. */
+int sbd_py_diag_loop_f32(int timestep_number0, int nrec, const float* lsm, const float* ci, const float* lon,
+                         const float* lat, const float* z, const float* std, const float* p, const float* u,
+                         const float* v, const float* theta, const float* ws0, const float* wd0,
+                         float target_plev, float thresh_wind, float thresh_winddir, float thresh_windch,
+                         float thresh_thc, float target_time, float maxdist, float timestep, int nps, int nlons,
+                         int nlats, float* output, uint8_t* flags);
+
 /* nt = get_threads()  S:195-206: here the number of CUDA devices. */
 int sbd_get_threads(void);
 

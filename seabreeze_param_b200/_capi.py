@@ -17,7 +17,7 @@ SYMBOLS = [
     "sbd_default_params", "sbd_last_error", "sbd_device_count",
     "sbd_get_edges_f32", "sbd_get_dist_f32", "sbd_sigmoid_f32", "sbd_seabreeze_diag_f32",
     "sbd_swap_bounds_f32", "sbd_swap_bounds_ew_f32", "sbd_swap_bounds_dev_f32",
-    "sbd_py_get_edges_f32", "sbd_py_get_dist_f32", "sbd_py_sigmoid_f32", "sbd_py_diag_f32",
+    "sbd_py_get_edges_f32", "sbd_py_get_dist_f32", "sbd_py_sigmoid_f32", "sbd_py_diag_f32", "sbd_py_diag_loop_f32",
     "sbd_get_threads",
     "sbd_plan_create", "sbd_plan_destroy", "sbd_plan_set_stream", "sbd_plan_use_own_stream", "sbd_plan_get_stream",
     "sbd_plan_sync", "sbd_plan_set_static", "sbd_plan_info", "sbd_plan_n_quads", "sbd_plan_step", "sbd_plan_step_scan", "sbd_plan_step_finish", "sbd_plan_step_py",
@@ -77,6 +77,7 @@ def load():
     lib.sbd_py_sigmoid_f32.argtypes = [fp, i, i, fp]
     lib.sbd_py_diag_f32.argtypes = [i, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, f, f, f, f, f, f, f, f, i, i, i,
                                     fp, vp]
+    lib.sbd_py_diag_loop_f32.argtypes = [i, i] + [fp] * 12 + [f] * 8 + [i, i, i, fp, vp]
     lib.sbd_plan_create.argtypes = [C.POINTER(vp), i, i, i, i, i, C.POINTER(SbdParams)]
     lib.sbd_plan_destroy.argtypes = [vp]
     lib.sbd_plan_destroy.restype = None

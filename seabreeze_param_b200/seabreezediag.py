@@ -20,6 +20,7 @@ import warnings
 
 import numpy as np
 
+from . import _capi
 from . import seabreeze as _sb
 
 
@@ -93,3 +94,41 @@ def diag(tt, lsm, z, std, lon, lat, pres, *args, **kwargs):
         thc, ws, wd = planes[1], planes[2], planes[3]
         tt += 1
     return tt, result[0], thc, ws, wd
+
+
+def diag_batched(tt, lsm, z, std, lon, lat, pres, u, v, t, ci=None, ws=None, wd=None, thc=None,
+                 target_plev=700.0, thresh_wind=11.0, thresh_winddir=90.0, thresh_windch=5.0, thresh_thc=0.75,
+                 target_time=6.0, maxdist=180.0, timestep=24.0, return_flags=False):
+    """Same result as ``diag`` for inputs with a time axis, computed by ONE call of the C-ABI
+    (sbd_py_diag_loop_f32): the per-record get_edges -> get_dist -> diag sequence of I:219-245 runs
+    on the device with the state threaded between records there, and the coast distance is only
+    recomputed for records whose ice field changed.  u, v: (time, pres, lat, lon); t, ci: (time, lat,
+    lon); arrays may be numpy (host) or torch CUDA tensors (float32, C-contiguous).
+
+    Returns tt, sb_con (time, lat, lon), thc(=t0 of the last record), ws, wd [, flags]."""
+    tt = max(1, int(tt))
+    f32 = lambda a: a if hasattr(a, "data_ptr") else np.ascontiguousarray(a, dtype=np.float32)
+    lsm, z, std, u, v, t = (f32(a) for a in (lsm, z, std, u, v, t))
+    lon, lat, pres = (np.ascontiguousarray(a, dtype=np.float32) for a in (lon, lat, pres))
+    nrec, nps, nlat, nlon = u.shape
+    if tuple(v.shape) != (nrec, nps, nlat, nlon) or tuple(t.shape) != (nrec, nlat, nlon):
+        raise ValueError("diag_batched: u, v must be (time, pres, lat, lon) and t (time, lat, lon)")
+    if ci is not None:
+        ci = f32(_unmask(ci))
+        if tuple(ci.shape) != (nrec, nlat, nlon):
+            raise ValueError("diag_batched: ci must be (time, lat, lon)")
+    ws = _state(ws, lsm, "Windspeed", tt)
+    wd = _state(wd, lsm, "Wind direction", tt)
+    _state(thc, lsm, "Heating contrast", tt)   # warns like diag(); the kernels never read thc
+    ws, wd = f32(ws), f32(wd)
+    out = np.empty((nrec, 4, nlat, nlon), dtype=np.float32)
+    flags = np.zeros((nrec, nlat, nlon), dtype=np.uint8) if return_flags else None
+    lib = _capi.load()
+    q = _capi.ptr
+    _capi.check(lib.sbd_py_diag_loop_f32(tt, nrec, q(lsm), q(ci), q(lon), q(lat), q(z), q(std), q(pres), q(u), q(v),
+                                         q(t), q(ws), q(wd), float(target_plev), float(thresh_wind),
+                                         float(thresh_winddir), float(thresh_windch), float(thresh_thc),
+                                         float(target_time), float(maxdist), float(timestep), nps, nlon, nlat,
+                                         q(out), q(flags)), "diag_batched")
+    res = (tt + nrec, out[:, 0].astype(np.float64), out[-1, 1], out[-1, 2], out[-1, 3])
+    return res + (flags,) if return_flags else res

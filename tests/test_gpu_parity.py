@@ -147,6 +147,36 @@ def test_py_wrapper_diag_matches_manual_loop(oracle):
     assert_bits_equal(ws_o, ws, "ws"); assert_bits_equal(wd_o, wd, "wd"); assert_bits_equal(o[1], thc, "t0")
 
 
+def test_py_batched_time_loop(oracle):
+    """seabreezediag.diag_batched (one C-ABI call for the whole time loop) ==
+    the reference's per-record loop on the oracle, with ice that changes on some records only."""
+    cfg = synth.CONFIGS["t_py"]
+    land, ice, lon, lat, z, sig = synth.static_fields(cfg)
+    nrec = 5
+    T, U, V, CI = [], [], [], []
+    for step in range(1, nrec + 1):
+        theta, p, u, v = synth.step_fields(cfg, step, land, z, lat)
+        T.append(theta); U.append(u); V.append(v)
+        CI.append(ice * (1.0 if step in (1, 2, 5) else 0.4))   # records 1,2 share ice; 3,4 share; 5 differs
+    T, U, V, CI = (np.stack(x).astype(np.float32) for x in (T, U, V, CI))
+    tt, sb, thc, ws, wd, fl = seabreezediag.diag_batched(1, land, z, sig, lon, lat, p, U, V, T, CI,
+                                                          timestep=cfg.timestep, return_flags=True)
+    assert tt == nrec + 1 and sb.shape == (nrec, cfg.ny, cfg.nx)
+    ws_o = np.zeros_like(z); wd_o = np.zeros_like(z)
+    for r in range(nrec):
+        cd = oracle.py_get_dist(oracle.py_get_edges(land, CI[r]), land, lon, lat)
+        o, f = oracle.py_diag(r + 1, p, z, sig, T[r], V[r], U[r], cd, ws_o, wd_o, timestep=cfg.timestep)
+        assert_bits_equal(o[0], sb[r].astype(np.float32), "sb_con record %d" % r)
+        assert np.array_equal(f, fl[r]), "flags record %d" % r
+        ws_o, wd_o = o[2].copy(), o[3].copy()
+    assert_bits_equal(ws_o, ws, "ws"); assert_bits_equal(wd_o, wd, "wd"); assert_bits_equal(o[1], thc, "t0")
+    # no ice at all, and the per-record wrapper gives the same answer
+    r1 = seabreezediag.diag_batched(1, land, z, sig, lon, lat, p, U, V, T, None, timestep=cfg.timestep)
+    r2 = seabreezediag.diag(1, land, z, sig, lon, lat, p, U, V, T, None, timestep=cfg.timestep)
+    assert_bits_equal(r1[1].astype(np.float32), r2[1].astype(np.float32), "batched vs per-record sb_con")
+    assert_bits_equal(r1[3], r2[3], "batched vs per-record ws")
+
+
 @pytest.mark.parametrize("name", ["t_gen", "c1"])
 def test_generic_edges_dist(oracle, name):
     cfg = synth.CONFIGS[name]

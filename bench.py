@@ -372,15 +372,18 @@ def main():
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        # p,u,v sit in pinned host memory and are gathered in place by the level scan (zero-copy):
-        # 16 B per quad and level of p plus one level of u and v cross PCIe; theta and the three
-        # state planes are staged by cudaMemcpyAsync, the four result planes + flags come back
-        nq = info["n_quads"]
-        h2d = 16 * nq * (nz + 2) + 4 * ((nx + 2 * h) * (ny + 2 * h) + 3 * n_cells)
+        # p,u,v sit in pinned host memory.  p: the northern rows of every level travel by DMA, the
+        # southern quads' columns are gathered in place by the level scan (zero-copy, 16 B per quad
+        # and level); u,v: one level per quad, zero-copy; theta and the three state planes are
+        # staged by cudaMemcpyAsync; the four result planes + flags come back
+        nq, nqn, ysp = info["n_quads"], info["n_quads_north"], info["host_split_row"]
+        h2d = (4 * ysp * nx * nz + 16 * (nq - nqn) * nz + 16 * nq * 2
+               + 4 * ((nx + 2 * h) * (ny + 2 * h) + 3 * n_cells))
         d2h = 4 * (4 * n_cells) + n_cells
         e2e = {"value": world * n_cells * ne / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": ne, "ms_per_step": 1e3 * dt / ne,
-               "api": "Plan.step with numpy arrays in pinned host memory (blocking call)",
+               "api": "Plan.step with numpy arrays in pinned host memory (blocking call); p: DMA of the northern "
+                      "rows + zero-copy gather of the southern columns",
                "host_input_bytes_per_step": 4 * (3 * n_cells * nz + (nx + 2 * h) * (ny + 2 * h) + 3 * n_cells)}
 
     if rank != 0:

@@ -20,7 +20,7 @@ SYMBOLS = [
     "sbd_py_get_edges_f32", "sbd_py_get_dist_f32", "sbd_py_sigmoid_f32", "sbd_py_diag_f32", "sbd_py_diag_loop_f32",
     "sbd_get_threads",
     "sbd_plan_create", "sbd_plan_destroy", "sbd_plan_set_stream", "sbd_plan_use_own_stream", "sbd_plan_get_stream",
-    "sbd_plan_sync", "sbd_plan_set_static", "sbd_plan_info", "sbd_plan_n_quads", "sbd_plan_step", "sbd_plan_step_scan", "sbd_plan_step_finish", "sbd_plan_step_py",
+    "sbd_plan_sync", "sbd_plan_set_static", "sbd_plan_info", "sbd_plan_n_quads", "sbd_plan_host_split", "sbd_plan_step", "sbd_plan_step_scan", "sbd_plan_step_finish", "sbd_plan_step_py",
     "sbd_launch_count", "sbd_stats_chain_f32", "sbd_plan_set_timing", "sbd_plan_last_timing", "sbd_plan_set_halo_mode", "sbd_plan_set_peer_theta",
 ]
 
@@ -89,6 +89,7 @@ def load():
     lib.sbd_plan_set_static.argtypes = [vp, fp, fp, fp, fp]
     lib.sbd_plan_info.argtypes = [vp, ip, ip, fp]
     lib.sbd_plan_n_quads.argtypes = [vp]
+    lib.sbd_plan_host_split.argtypes = [vp, ip, ip]
     lib.sbd_plan_step.argtypes = [vp, f, i, fp, fp, fp, fp, fp, fp, fp, fp, vp]
     lib.sbd_plan_step_scan.argtypes = [vp, fp, fp, fp]
     lib.sbd_plan_step_finish.argtypes = [vp, f, i, fp, fp, fp, fp, fp, vp]

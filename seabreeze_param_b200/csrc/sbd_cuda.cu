@@ -19,6 +19,7 @@
 #include <atomic>
 #include <mutex>
 #include <vector>
+#include <algorithm>
 
 #include "sbd.h"
 #include "sbd_math.h"
@@ -1458,6 +1459,12 @@ struct sbd_plan {
   float* d_nwd = nullptr;     // scratch: wind direction at the selected level
   bool scan_done = false;     // sbd_plan_step_scan has been issued for the current step
   int last_order = 0;         // kernel order used by the last generic step (see TrigArgs::order)
+  // host-buffer steps with pinned p: the northern rows [0, ysplit) of every level travel by DMA
+  // into d_pfull while the level scan of the southern rows gathers its columns over PCIe in place
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t e_copy = nullptr, e_main = nullptr;
+  float* d_pfull = nullptr;
+  int ysplit = 0, n_quads_top = 0;
   const float *peer_up = nullptr, *peer_dn = nullptr;  // neighbour ranks' theta planes (peer-mapped)
   int peer_ny_up = 0;
   const float *cur_p = nullptr, *cur_u = nullptr, *cur_v = nullptr;
@@ -1626,10 +1633,10 @@ bool scan_vec_ok(const sbd_plan* p, const TrigArgs& a)
 }
 
 template <int G, int QNT>
-int launch_scan_quad(sbd_plan* p, const TrigArgs& a, int qsmem, bool pdl)
+int launch_scan_quad(sbd_plan* p, const TrigArgs& a, int qsmem, bool pdl, int q0, int q1)
 {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cdiv(p->n_quads, QNT));
+  cfg.gridDim = dim3(cdiv(q1 - q0, QNT));
   cfg.blockDim = dim3(QNT);
   cfg.dynamicSmemBytes = qsmem;
   cfg.stream = p->stream;
@@ -1638,14 +1645,16 @@ int launch_scan_quad(sbd_plan* p, const TrigArgs& a, int qsmem, bool pdl)
   at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  const int* quads = p->d_quads;
-  int nq = p->n_quads;
+  const int* quads = p->d_quads + q0;
+  int nq = q1 - q0;
   CK(cudaLaunchKernelEx(&cfg, k_scan_quad<G, QNT>, a, quads, nq));
   return SBD_OK;
 }
 
-int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false)
+// q0, q1: range of the compacted quad list to process (default: all of it)
+int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false, int q0 = 0, int q1 = -1)
 {
+  if (q1 < 0) q1 = p->n_quads;
   a.nws = p->d_nws;
   a.nwd = p->d_nwd;
   if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
@@ -1680,13 +1689,15 @@ int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false)
         }
       }
       const bool use_pdl = pdl && !p->timing;
-      int rc;
-      if (G == 5) rc = launch_scan_quad<5, QNT>(p, a, qsmem, use_pdl);
-      else if (G == 7) rc = launch_scan_quad<7, QNT>(p, a, qsmem, use_pdl);
-      else if (G == 10) rc = launch_scan_quad<10, QNT>(p, a, qsmem, use_pdl);
-      else rc = launch_scan_quad<14, QNT>(p, a, qsmem, use_pdl);
-      if (rc) return rc;
-      LAUNCHED();
+      int rc = SBD_OK;
+      if (q1 > q0) {
+        if (G == 5) rc = launch_scan_quad<5, QNT>(p, a, qsmem, use_pdl, q0, q1);
+        else if (G == 7) rc = launch_scan_quad<7, QNT>(p, a, qsmem, use_pdl, q0, q1);
+        else if (G == 10) rc = launch_scan_quad<10, QNT>(p, a, qsmem, use_pdl, q0, q1);
+        else rc = launch_scan_quad<14, QNT>(p, a, qsmem, use_pdl, q0, q1);
+        if (rc) return rc;
+        LAUNCHED();
+      }
     } else {
       k_scan_scalar<14><<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
     }
@@ -1893,6 +1904,10 @@ void sbd_plan_destroy(sbd_plan* p)
   cudaFree(p->d_gzsm); cudaFree(p->d_code); cudaFree(p->d_stats); cudaFree(p->d_carry); cudaFree(p->d_cnt);
   cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads); cudaFree(p->d_nws); cudaFree(p->d_nwd);
   for (int i = 0; i < 6; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+  if (p->e_copy) cudaEventDestroy(p->e_copy);
+  if (p->e_main) cudaEventDestroy(p->e_main);
+  cudaFree(p->d_pfull);
   for (auto& s : p->stage) cudaFree(s.first);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
@@ -2028,6 +2043,22 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
   if (p->variant == SBD_VARIANT_GENERIC && cnt[2] != cnt[1])
     return fail(SBD_ECUDA, "internal: compaction count differs from the coastal-cell count");
   p->R = (p->nn_max <= 16) ? p->nn_max : min(p->nn_max, 56);  // see launch_trigger
+  // split row of the hybrid host path (SBD_E2E_SPLIT = fraction of rows that travel by DMA)
+  p->ysplit = 0; p->n_quads_top = 0;
+  if (p->variant == SBD_VARIANT_GENERIC && p->n_quads > 0) {
+    static float frac = -1.0f;
+    if (frac < 0.0f) { const char* e = getenv("SBD_E2E_SPLIT"); frac = e ? (float)atof(e) : 0.9f; if (frac > 1.0f) frac = 1.0f; }
+    p->ysplit = (int)(frac * p->ny);
+    if (p->ysplit > 0) {
+      std::vector<int> hq(p->n_quads);
+      CK(cudaMemcpyAsync(hq.data(), p->d_quads, sizeof(int) * p->n_quads, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const long long lim = ((long long)p->ysplit * p->nx) / 4;  // first quad that is not wholly north of the split
+      p->n_quads_top = (int)(std::lower_bound(hq.begin(), hq.end(), (int)lim) - hq.begin());
+      p->ysplit = (int)((lim * 4) / p->nx);                      // rows fully covered by quads [0, n_quads_top)
+      if (((lim * 4) % p->nx) != 0) p->ysplit += 1;              // the split quad's row is copied too
+    }
+  }
   return SBD_OK;
 }
 
@@ -2060,6 +2091,13 @@ int sbd_plan_info(sbd_plan* p, int* nn_max, int* n_coastal, float* stats4)
 }
 
 int sbd_plan_n_quads(sbd_plan* p) { return (p && p->have_static) ? p->n_quads : -1; }
+int sbd_plan_host_split(sbd_plan* p, int* ysplit, int* n_quads_north)
+{
+  if (!p || !p->have_static) return fail(SBD_EINVAL, "plan has no static fields yet");
+  if (ysplit) *ysplit = p->ysplit;
+  if (n_quads_north) *n_quads_north = p->n_quads_top;
+  return SBD_OK;
+}
 
 static int six_hourly_flag(int step, float timestep_s, float target_time)
 {
@@ -2161,6 +2199,31 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
     return flush_out(p, pend, any_host);
   }
   a.order = 1; p->last_order = 1;
+  // Hybrid transfer for pinned host p: while the scan of the southern quads gathers its pressure
+  // columns over PCIe in place (zero-copy), the DMA engine copies the northern rows of every
+  // level into device memory; the northern quads are scanned from HBM afterwards.  Both halves
+  // of the link's read bandwidth are used, and each cell's column crosses PCIe exactly once.
+  const bool p_mapped = !is_device_ptr(pp) && a.p != nullptr && mapped_host_ptr(pp) == a.p;
+  if (p_mapped && p->n_quads_top > 0 && !p->timing) {
+    if (!p->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&p->e_copy, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&p->e_main, cudaEventDisableTiming));
+      CK(cudaMalloc((void**)&p->d_pfull, n3 * sizeof(float)));
+    }
+    CK(cudaEventRecord(p->e_main, p->stream));            // previous users of d_pfull are done
+    CK(cudaStreamWaitEvent(p->copy_stream, p->e_main, 0));
+    CK(cudaMemcpy2DAsync(p->d_pfull, n2 * sizeof(float), pp, n2 * sizeof(float),
+                         (size_t)p->ysplit * p->nx * sizeof(float), p->nz, cudaMemcpyHostToDevice, p->copy_stream));
+    CK(cudaEventRecord(p->e_copy, p->copy_stream));
+    if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
+    if ((rc = launch_scan(p, a, true, p->n_quads_top, p->n_quads))) return rc;   // south: zero-copy
+    CK(cudaStreamWaitEvent(p->stream, p->e_copy, 0));
+    TrigArgs b = a;
+    b.p = p->d_pfull;
+    if ((rc = launch_scan(p, b, false, 0, p->n_quads_top))) return rc;           // north: from HBM
+    return flush_out(p, pend, any_host);
+  }
   if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
   if ((rc = launch_scan(p, a, true))) return rc;
   return flush_out(p, pend, any_host);

@@ -168,7 +168,10 @@ class Plan:
         nn, nc = C.c_int(), C.c_int()
         st = np.zeros(4, dtype=np.float32)
         _capi.check(self.lib.sbd_plan_info(self._h, C.byref(nn), C.byref(nc), _capi.ptr(st)), "plan_info")
-        return {"nn_max": nn.value, "n_coastal": nc.value, "n_quads": int(self.lib.sbd_plan_n_quads(self._h)), "mean": float(st[0]), "std2inv": float(st[1]),
+        ys, qn = C.c_int(), C.c_int()
+        _capi.check(self.lib.sbd_plan_host_split(self._h, C.byref(ys), C.byref(qn)), "plan_host_split")
+        return {"nn_max": nn.value, "n_coastal": nc.value, "n_quads": int(self.lib.sbd_plan_n_quads(self._h)),
+                "host_split_row": ys.value, "n_quads_north": qn.value, "mean": float(st[0]), "std2inv": float(st[1]),
                 "r": float(st[2]), "var": float(st[3])}
 
     def step(self, timestep, timestep_number, p, u, v, theta, windspeed, winddir, thc, sb_con, flags=None):

@@ -264,6 +264,31 @@ def test_generic_virtual_halo(oracle):
     plan.close()
 
 
+def test_generic_pinned_host_buffers(oracle):
+    """Host arrays in pinned memory: p,u,v are gathered in place over PCIe (zero-copy) for the southern
+    rows while the DMA engine copies the northern rows (hybrid transfer) -- same bits as the oracle."""
+    import torch
+    cfg = synth.Config("t_pin", 256, 128, 10, 6, "generic", 5.0, False, 1440.0, "pinned-host test")
+    case = generic_case(cfg, oracle)
+    ny, nx = cfg.ny, cfg.nx
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
+    plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
+    assert plan.info()["n_quads"] > 0
+    so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    sp = [pin(np.zeros((ny, nx), np.float32)) for _ in range(4)]
+    for step in (1, 2, 15):
+        theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
+        fo = oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"],
+                                   case["sigma_h"], *so, cfg.h)
+        fp = torch.zeros((ny, nx), dtype=torch.uint8).pin_memory().numpy()
+        plan.step(cfg.timestep, step, pin(p), pin(u), pin(v), pin(theta_h), *sp, flags=fp)
+        for a, b, nm in zip(so, sp, ("windspeed", "winddir", "thc", "sb_con")):
+            assert_bits_equal(a, b, "%s step %d" % (nm, step))
+        assert np.array_equal(fo, fp)
+    plan.close()
+
+
 def test_generic_device_pointers_torch(oracle):
     """Same step with every array resident on the GPU (torch tensors): the path bench.py times."""
     import torch

@@ -215,7 +215,9 @@ int sbd_plan_step_py(sbd_plan* plan, int timestep_number, float timestep_min, co
  * kernels are launched on.  While timing is on the two kernels of the generic step run strictly
  * one after the other (no programmatic dependent launch), so each duration is that kernel alone:
  * ms3[0] = window kernel (k_trigger), ms3[1] = level-scan kernel (k_scan_quad),
- * ms3[2] = threshold kernel (k_final).  Python variant: one kernel, ms3[1] = ms3[2] = 0. */
+ * ms3[2] = threshold kernel (k_final).  When the step runs as the single fused kernel
+ * (k_step_fused: coarse grids, device-resident p) and for the python variant: ms3[0] = that one
+ * kernel, ms3[1] = ms3[2] = 0. */
 int sbd_plan_set_timing(sbd_plan* plan, int on);
 int sbd_plan_last_timing(sbd_plan* plan, float* ms3);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */

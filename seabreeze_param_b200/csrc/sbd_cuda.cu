@@ -945,6 +945,75 @@ __device__ __forceinline__ void window_fixed(const float* __restrict__ s_t0, con
   }
 }
 
+// n_thc of one coastal-zone cell of a staged tile: sequential raster sum over its final (2nn+1)^2
+// window, bit-identical to the last pass of the reference's growing search (G:191-214), then G:216.
+// ent = land << 31 | bucket << 16 | local id (bucket NB-1: wider than the tile halo -> global path).
+template <int VARIANT, int NB>
+__device__ __forceinline__ float cell_thc(const TrigArgs& a, const float* __restrict__ s_t0,
+                                          const uint32_t* __restrict__ s_bits, int W, int WBITS, int R, uint32_t ent,
+                                          int lx, int ly, int gx, int gy, int so)
+{
+  const int bkt = (int)((ent >> 16) & 0x7fffu);
+  const bool land_c = (ent >> 31) != 0;
+  int nn = bkt;
+  float T_l = 0.0f, T_s = 0.0f;
+  uint32_t c_l = 0, c_s = 0;
+  if (bkt != NB - 1) {
+    const int lcx = R + lx, lcy = R + ly;
+    switch (nn) {
+      case 1: window_fixed<1>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+      case 2: window_fixed<2>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+      case 3: window_fixed<3>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+      case 4: window_fixed<4>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+      case 5: window_fixed<5>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+      case 6: window_fixed<6>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+      case 7: window_fixed<7>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+      case 8: window_fixed<8>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
+      default: {
+        const int wlen = 2 * nn + 1;
+        for (int ii = lcy - nn; ii <= lcy + nn; ++ii) {
+          int bpos = ii * WBITS + lcx - nn;
+          const float* tp = s_t0 + ii * W + lcx - nn;
+          int rem = wlen;
+          while (rem > 0) {
+            const int cnt = min(rem, 32);
+            uint32_t bits = __funnelshift_r(s_bits[bpos >> 5], s_bits[(bpos >> 5) + 1], bpos & 31);
+            if (cnt < 32) bits &= (1u << cnt) - 1u;
+            c_l += __popc(bits);
+            int j = 0;
+            for (; j + 8 <= cnt; j += 8) {
+#pragma unroll
+              for (int uu = 0; uu < 8; ++uu) {
+                const float t = tp[j + uu];
+                if (bits & (1u << uu)) T_l = T_l + t;   // G:200-202
+                else T_s = T_s + t;                     // G:204-205
+              }
+              bits >>= 8;
+            }
+            for (; j < cnt; ++j) {
+              const float t = tp[j];
+              if (bits & 1u) T_l = T_l + t;
+              else T_s = T_s + t;
+              bits >>= 1;
+            }
+            bpos += cnt; tp += cnt; rem -= cnt;
+          }
+        }
+      }
+    }
+    const int wl = 2 * nn + 1;
+    c_s = (uint32_t)(wl * wl) - c_l;
+  } else {
+    nn = (int)(a.code[so] & 0x7fffu);
+    window_sums_global<VARIANT>(a, gx, gy, nn, T_l, T_s, c_l, c_s);
+  }
+  // n_l, n_s are fp32 counters in the reference: n = n + 1 saturates at 2^24
+  const float n_l = (float)min(c_l, 16777216u), n_s = (float)min(c_s, 16777216u);
+  const float mul = land_c ? 1.0f : -1.0f;                    // G:182-186
+  const float n_thc = mul * ((T_l / n_l) - (T_s / n_s));      // G:216
+  return n_thc;
+}
+
 // K4a window kernel.
 //   phase 1  stage t0 = theta - gzsm (G:167) and the land bit of the tile + halo R in shared memory
 //   phase 2  every thread classifies its cells; coastal-zone cells go into a shared work list
@@ -1102,64 +1171,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
     const int ly = lid / TX, lx = lid - ly * TX;
     const int gx = x0 + lx, gy = y0 + ly;
     const int so = own_index<VARIANT>(a.g, gx, gy);
-    const int bkt = (int)((ent >> 16) & 0x7fffu);
-    const bool land_c = (ent >> 31) != 0;
-    int nn = bkt;
-    float T_l = 0.0f, T_s = 0.0f;
-    uint32_t c_l = 0, c_s = 0;
-    if (bkt != NB - 1) {
-      const int lcx = R + lx, lcy = R + ly;
-      switch (nn) {
-        case 1: window_fixed<1>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
-        case 2: window_fixed<2>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
-        case 3: window_fixed<3>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
-        case 4: window_fixed<4>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
-        case 5: window_fixed<5>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
-        case 6: window_fixed<6>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
-        case 7: window_fixed<7>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
-        case 8: window_fixed<8>(s_t0, s_bits, W, WBITS, lcx, lcy, T_l, T_s, c_l); break;
-        default: {
-          const int wlen = 2 * nn + 1;
-          for (int ii = lcy - nn; ii <= lcy + nn; ++ii) {
-            int bpos = ii * WBITS + lcx - nn;
-            const float* tp = s_t0 + ii * W + lcx - nn;
-            int rem = wlen;
-            while (rem > 0) {
-              const int cnt = min(rem, 32);
-              uint32_t bits = __funnelshift_r(s_bits[bpos >> 5], s_bits[(bpos >> 5) + 1], bpos & 31);
-              if (cnt < 32) bits &= (1u << cnt) - 1u;
-              c_l += __popc(bits);
-              int j = 0;
-              for (; j + 8 <= cnt; j += 8) {
-#pragma unroll
-                for (int uu = 0; uu < 8; ++uu) {
-                  const float t = tp[j + uu];
-                  if (bits & (1u << uu)) T_l = T_l + t;   // G:200-202
-                  else T_s = T_s + t;                     // G:204-205
-                }
-                bits >>= 8;
-              }
-              for (; j < cnt; ++j) {
-                const float t = tp[j];
-                if (bits & 1u) T_l = T_l + t;
-                else T_s = T_s + t;
-                bits >>= 1;
-              }
-              bpos += cnt; tp += cnt; rem -= cnt;
-            }
-          }
-        }
-      }
-      const int wl = 2 * nn + 1;
-      c_s = (uint32_t)(wl * wl) - c_l;
-    } else {
-      nn = (int)(a.code[so] & 0x7fffu);
-      window_sums_global<VARIANT>(a, gx, gy, nn, T_l, T_s, c_l, c_s);
-    }
-    // n_l, n_s are fp32 counters in the reference: n = n + 1 saturates at 2^24
-    const float n_l = (float)min(c_l, 16777216u), n_s = (float)min(c_s, 16777216u);
-    const float mul = land_c ? 1.0f : -1.0f;                    // G:182-186
-    const float n_thc = mul * ((T_l / n_l) - (T_s / n_s));      // G:216
+    const float n_thc = cell_thc<VARIANT, NB>(a, s_t0, s_bits, W, WBITS, R, ent, lx, ly, gx, gy, so);
     const size_t c = (size_t)gy * a.g.nx + gx;
     if (SPLIT) {
       // generic: n_thc goes straight into the caller's thc array (state update G:262); the
@@ -1391,6 +1403,256 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4 fused step (generic variant, coarse grids): ONE launch per timestep.  A CTA owns a 64x16-cell
+// tile and splits into two roles that run side by side on the same SM:
+//   warps 0..7  (256 threads)  window role: stage t0 + land bits of the tile and its halo, bucket
+//                               the coastal cells by nn, sequential window sums -> n_thc (as k_trigger)
+//   warps 8..11 (128 threads)  scan role:   the tile's 256 aligned quads, two per thread, pressure
+//                               columns streamed with cp.async (G levels x 2 groups x 2 quads in
+//                               flight per thread), first minimum of |p - target|, u,v at that level
+//                               -> n_ws, n_wd (as k_scan_quad)
+// The scan warps are almost always stalled on HBM, the window warps on shared memory / issue
+// slots, so the two overlap on every SM by construction (no second launch, no dependent-launch
+// scheduling, no scratch planes).  The roles meet at one block barrier; then all 384 threads apply
+// thresholds, scaling and the state update (G:235-266) to the tile's coastal cells.
+// Needs nx % 4 == 0, 16-byte aligned p,u,v and R <= RMAX.
+// ------------------------------------------------------------------------------------------------
+template <int TX, int TY, int RMAX, int G>
+__global__ void __launch_bounds__(384, 3) k_step_fused(const TrigArgs a)
+{
+  constexpr int NWIN = 256, NSCAN = 128, NTHR = NWIN + NSCAN;
+  constexpr int NCELL = TX * TY, NQ = NCELL / 4, QPT = NQ / NSCAN, QROW = TX / 4;
+  constexpr int CPT = NCELL / NWIN;
+  constexpr int NB = 64;
+  constexpr int VARIANT = SBD_VARIANT_GENERIC;
+  static_assert(QPT == 2 && TX % 32 == 0 && NCELL % NWIN == 0 && NWIN % TX == 0, "tile shape");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int R = a.R;
+  const int W = TX + 2 * R, Hh = TY + 2 * R;
+  const int total = W * Hh;
+  const int WBW = (W + 31) >> 5, WBITS = WBW * 32;
+  float4* s_buf = reinterpret_cast<float4*>(smem_raw);                 // [2][G][NSCAN]
+  float* s_thc = reinterpret_cast<float*>(s_buf + 2 * G * NSCAN);        // [NCELL]
+  float* s_nws = s_thc + NCELL;
+  float* s_nwd = s_nws + NCELL;
+  uint32_t* s_list = reinterpret_cast<uint32_t*>(s_nwd + NCELL);        // [NCELL]
+  float* s_t0 = reinterpret_cast<float*>(s_list + NCELL);               // [total]
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_t0 + total);         // [Hh*WBW + 2]
+  __shared__ int s_cnt[NB];
+  __shared__ int s_off[NB];
+  __shared__ int s_nlist;
+  __shared__ uint16_t s_qlist[NQ];   // scan role: local ids of the tile's quads with a coastal cell
+
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int tid = threadIdx.x;
+  const size_t n2 = (size_t)a.g.nx * a.g.ny;
+
+  if (tid >= NWIN) {
+    // ============================== scan role ==============================
+    // 1. compact the tile's quads that hold a coastal cell; 2. warps pull chunks of 32 quads from
+    //    that list, one quad per lane, G levels x 2 groups in flight per lane.
+    const int st = tid - NWIN;
+    const int lane = st & 31;
+    const float tp = a.prm.target_plev;
+    const int nz = a.nz;
+    const size_t stride4 = n2 >> 2;
+    const int ngroups = (nz + G - 1) / G;
+    // every scan warp owns 64 consecutive quads of the tile (4 tile rows) and compacts the ones with
+    // a coastal cell into its own slice of s_qlist: warp-local, no block-level synchronisation
+    const int sw = st >> 5;
+    int nact = 0;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+      const int lq = sw * (NQ / 4) + q * 32 + lane;
+      const int ly = lq / QROW, lxq = lq - ly * QROW;
+      const int gx0 = x0 + lxq * 4, gy = y0 + ly;
+      bool anyc = false;
+      if (gx0 < a.g.nx && gy < a.g.ny) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          anyc |= (a.code[(size_t)(gy + a.g.h) * a.g.ldx + (gx0 + j + a.g.h)] & 0x7fffu) != 0;
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, anyc);
+      if (anyc) s_qlist[sw * (NQ / 4) + nact + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)lq;
+      nact += __popc(bal);
+    }
+    __syncwarp();
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    for (int chunk = 0; chunk < nact; chunk += 32) {
+      const int ent = chunk + lane;
+      const bool have = ent < nact;
+      const int lq = have ? (int)s_qlist[sw * (NQ / 4) + ent] : 0;
+      const int ly = lq / QROW, lxq = lq - ly * QROW;
+      const int c0 = (y0 + ly) * a.g.nx + x0 + lxq * 4;
+      const int m = c0 >> 2;
+      const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
+      auto issue = [&](int g) {
+        const int kbase = g * G;
+        if (have) {
+          float4* dst = s_buf + (size_t)((g & 1) * G) * NSCAN + st;
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            if (kbase + j < nz) {
+              const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)j * NSCAN);
+              asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa),
+                           "l"(pq + (size_t)(kbase + j) * stride4), "l"(pol)
+                           : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+      };
+      issue(0);
+      float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+      int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+      for (int g = 0; g < ngroups; ++g) {
+        if (g + 1 < ngroups) {
+          issue(g + 1);
+          asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        if (have) {
+          const float4* src = s_buf + (size_t)((g & 1) * G) * NSCAN + st;
+          const int kbase = g * G;
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int kk = kbase + j;
+            if (kk < nz) {
+              const float4 d = src[(size_t)j * NSCAN];
+              const float e0 = fabsf(d.x - tp), e1 = fabsf(d.y - tp), e2 = fabsf(d.z - tp), e3 = fabsf(d.w - tp);
+              // minloc(abs(p - target_plev)): level 0 initialises, later levels need a strict < (G:223)
+              if (kk == 0 || e0 < b0) { b0 = e0; l0 = kk; }
+              if (kk == 0 || e1 < b1) { b1 = e1; l1 = kk; }
+              if (kk == 0 || e2 < b2) { b2 = e2; l2 = kk; }
+              if (kk == 0 || e3 < b3) { b3 = e3; l3 = kk; }
+            }
+          }
+        }
+      }
+      if (have) {
+        // wind at the selected levels (G:225-227) -> shared memory
+        const int lv[4] = {l0, l1, l2, l3};
+        float uu[4], vv[4];
+        if (l0 == l1 && l1 == l2 && l2 == l3) {
+          const float4 u4 = __ldcs(reinterpret_cast<const float4*>(a.u + (size_t)l0 * n2) + m);
+          const float4 v4 = __ldcs(reinterpret_cast<const float4*>(a.v + (size_t)l0 * n2) + m);
+          uu[0] = u4.x; uu[1] = u4.y; uu[2] = u4.z; uu[3] = u4.w;
+          vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uu[j] = __ldcs(a.u + (size_t)lv[j] * n2 + c0 + j);
+            vv[j] = __ldcs(a.v + (size_t)lv[j] * n2 + c0 + j);
+          }
+        }
+        const int lbase = ly * TX + lxq * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float n_ws, n_wd;
+          wind_from_uv(a, uu[j], vv[j], n_ws, n_wd);
+          s_nws[lbase + j] = n_ws;
+          s_nwd[lbase + j] = n_wd;
+        }
+      }
+    }
+  } else {
+    // ============================== window role ==============================
+    if (tid < NB) s_cnt[tid] = 0;
+    {
+      constexpr int MAXC = (TX + 2 * RMAX + 31) / 32;
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int ly = warp; ly < Hh; ly += NWIN / 32) {
+        float th[MAXC], gz[MAXC];
+        uint32_t cd[MAXC];
+#pragma unroll
+        for (int cch = 0; cch < MAXC; ++cch) {
+          const int lx = cch * 32 + lane;
+          th[cch] = 0.0f; gz[cch] = 0.0f; cd[cch] = 0u;
+          if (lx < W) {
+            const int sidx = nbr_index<VARIANT>(a.g, x0 - R + lx, y0 - R + ly);
+            th[cch] = load_theta<VARIANT>(a, x0 - R + lx, y0 - R + ly, sidx);
+            gz[cch] = a.gzsm[sidx];
+            cd[cch] = a.code[sidx];
+          }
+        }
+#pragma unroll
+        for (int cch = 0; cch < MAXC; ++cch) {
+          const int lx = cch * 32 + lane;
+          if (lx < W) s_t0[ly * W + lx] = th[cch] - gz[cch];  // G:167
+          const uint32_t bb = __ballot_sync(0xffffffffu, (cd[cch] >> 15) != 0);
+          if (lane == 0 && cch * 32 < WBITS) s_bits[ly * WBW + cch] = bb;
+        }
+      }
+      if (tid < 2) s_bits[Hh * WBW + tid] = 0u;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int cx = tid % TX;
+    const int cy0 = (tid / TX) * CPT;
+    uint32_t my_code[CPT];
+    int my_slot[CPT];
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+      const int gx = x0 + cx, gy = y0 + cy0 + q;
+      my_code[q] = 0;
+      my_slot[q] = -1;
+      if (gx >= a.g.nx || gy >= a.g.ny) continue;
+      const uint32_t cd = a.code[own_index<VARIANT>(a.g, gx, gy)];
+      const int nn = (int)(cd & 0x7fffu);
+      my_code[q] = cd;
+      if (nn == 0) {  // outside the coastal zone (G:174-176)
+        const size_t c = (size_t)gy * a.g.nx + gx;
+        a.sb[c] = a.prm.missing;
+        if (a.flags) a.flags[c] = 0;
+      } else {
+        const int bkt = (nn <= R && nn < NB - 1) ? nn : NB - 1;
+        my_slot[q] = atomicAdd(&s_cnt[bkt], 1);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid == 0) {
+      int run = 0;
+      for (int k = 0; k < NB; ++k) { s_off[k] = run; run += s_cnt[k]; }
+      s_nlist = run;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+      if (my_slot[q] >= 0) {
+        const int nn = (int)(my_code[q] & 0x7fffu);
+        const int bkt = (nn <= R && nn < NB - 1) ? nn : NB - 1;
+        const int lid = (cy0 + q) * TX + cx;
+        s_list[s_off[bkt] + my_slot[q]] = ((my_code[q] & 0x8000u) << 16) | ((uint32_t)bkt << 16) | (uint32_t)lid;
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int n_list = s_nlist;
+    for (int e = tid; e < n_list; e += NWIN) {
+      const uint32_t ent = s_list[e];
+      const int lid = (int)(ent & 0xffffu);
+      const int ly = lid / TX, lx = lid - ly * TX;
+      const int gx = x0 + lx, gy = y0 + ly;
+      const int so = own_index<VARIANT>(a.g, gx, gy);
+      s_thc[lid] = cell_thc<VARIANT, NB>(a, s_t0, s_bits, W, WBITS, R, ent, lx, ly, gx, gy, so);
+    }
+  }
+  __syncthreads();
+  // ============================== thresholds: all threads ==============================
+  const int n_list = s_nlist;
+  for (int e = tid; e < n_list; e += NTHR) {
+    const int lid = (int)(s_list[e] & 0xffffu);
+    const int ly = lid / TX, lx = lid - ly * TX;
+    const size_t c = (size_t)(y0 + ly) * a.g.nx + (x0 + lx);
+    const float n_thc = s_thc[lid];
+    a.thc[c] = n_thc;                                                     // G:262
+    float wsp = 0.0f, wdp = 0.0f;
+    if (!a.first_step) { wsp = __ldcg(a.ws + c); wdp = __ldcg(a.wd + c); }
+    trigger_point_vals(a, c, n_thc, s_nws[lid], s_nwd[lid], wsp, wdp);
+  }
+}
+
 // K4c final: thresholds, scaling and state update (G:235-266) for every coastal-zone cell of the
 // compacted list, from n_thc (thc[], window kernel) and n_ws / n_wd (scratch planes, scan kernel).
 // An ordinary (fully stream-ordered) launch: it must see both the scan's and the window kernel's
@@ -1458,7 +1720,7 @@ struct sbd_plan {
   float* d_nws = nullptr;     // scratch: wind speed at the selected level (scan -> window kernel)
   float* d_nwd = nullptr;     // scratch: wind direction at the selected level
   bool scan_done = false;     // sbd_plan_step_scan has been issued for the current step
-  int last_order = 0;         // kernel order used by the last generic step (see TrigArgs::order)
+  int last_order = 0;         // kernel order used by the last generic step (see TrigArgs::order); 2 = fused kernel
   // host-buffer steps with pinned p: the northern rows [0, ysplit) of every level travel by DMA
   // into d_pfull while the level scan of the southern rows gathers its columns over PCIe in place
   cudaStream_t copy_stream = nullptr;
@@ -1947,8 +2209,8 @@ int sbd_plan_last_timing(sbd_plan* p, float* ms3)
   if (!p || !ms3 || !p->ev[0]) return fail(SBD_EINVAL, "timing was not enabled");
   ms3[0] = ms3[1] = ms3[2] = 0.0f;
   CK(cudaStreamSynchronize(p->stream));
-  CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));              // window kernel
-  if (p->variant == SBD_VARIANT_GENERIC) {
+  CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));              // window kernel (or the fused step kernel)
+  if (p->variant == SBD_VARIANT_GENERIC && p->last_order != 2) {
     CK(cudaEventElapsedTime(&ms3[1], p->ev[2], p->ev[3]));            // level-scan kernel
     if (p->last_order == 0) CK(cudaEventElapsedTime(&ms3[2], p->ev[4], p->ev[5]));  // threshold kernel
   }
@@ -2199,6 +2461,30 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
     return flush_out(p, pend, any_host);
   }
   a.order = 1; p->last_order = 1;
+  // Optional (SBD_FUSED=1): one fused, warp-specialised launch.  Measured on c2: 61.9 us per step
+  // against 51 us for the two-kernel path below -- a CTA holds its window warps' registers until
+  // its scan warps are done, which leaves only 12 streaming warps per SM -- so it is off by default.
+  {
+    static int fused_env = -1;
+    if (fused_env < 0) { const char* e = getenv("SBD_FUSED"); fused_env = e ? atoi(e) : 0; }
+    if (fused_env && a.R <= 16 && (p->nx % 4) == 0 && is_device_ptr(pp)) {
+      constexpr int TX = 64, TY = 16, G = 10;
+      const int R = a.R;
+      const size_t cells = (size_t)(TX + 2 * R) * (TY + 2 * R);
+      const size_t smem = (size_t)2 * G * 128 * 16 + (size_t)TX * TY * 4 * 4 + cells * 4 +
+                          ((size_t)(TY + 2 * R) * ((TX + 2 * R + 31) / 32) + 2) * 4;
+      auto kern = k_step_fused<TX, TY, 16, G>;
+      static bool attr = false;
+      if (!attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+      dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+      p->last_order = 2;
+      if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+      kern<<<grid, 384, smem, p->stream>>>(a); LAUNCHED();
+      if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+      CK(cudaGetLastError());
+      return flush_out(p, pend, any_host);
+    }
+  }
   // Hybrid transfer for pinned host p: while the scan of the southern quads gathers its pressure
   // columns over PCIe in place (zero-copy), the DMA engine copies the northern rows of every
   // level into device memory; the northern quads are scanned from HBM afterwards.  Both halves

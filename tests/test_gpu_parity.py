@@ -341,6 +341,43 @@ def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect):
     plan.close()
 
 
+def test_fused_step_kernel_variant():
+    """SBD_FUSED=1 selects the single fused (warp-specialised) step kernel; same bits as the default
+    two-kernel path.  The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+from oracle import oracle as O
+from seabreeze_param_b200 import generic, synth
+from util import generic_case, generic_step_inputs
+O.set_math(1)
+cfg = synth.Config("t_f", 192, 80, 9, 6, "generic", 5.0, False, 1440.0, "fused test")
+case = generic_case(cfg, O)
+dev = torch.device("cuda:0")
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+plan = generic.Plan(0, cfg.nx, cfg.ny, cfg.nz, cfg.h)
+plan.set_static(t(case["mask_h"]), t(case["z_h"]), t(case["sigma_h"]))
+so = [np.zeros((cfg.ny, cfg.nx), np.float32) for _ in range(4)]
+sg = [torch.zeros((cfg.ny, cfg.nx), dtype=torch.float32, device=dev) for _ in range(4)]
+fg = torch.zeros((cfg.ny, cfg.nx), dtype=torch.uint8, device=dev)
+for step in (1, 2, 15):
+    th, p, u, v = generic_step_inputs(cfg, case, step, O)
+    fo = O.seabreeze_diag(cfg.timestep, step, p, u, v, th, case["mask_h"], case["z_h"], case["sigma_h"], *so, cfg.h)
+    plan.step(cfg.timestep, step, t(p), t(u), t(v), t(th), *sg, flags=fg)
+    plan.sync()
+    for a, b in zip(so, sg):
+        b = b.cpu().numpy()
+        assert ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all()
+    assert np.array_equal(fo, fg.cpu().numpy())
+print("FUSED_OK")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, SBD_FUSED="1"))
+    assert r.returncode == 0 and "FUSED_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_determinism_run_twice(oracle):
     cfg = synth.CONFIGS["c5"]
     land, ice, lon, lat, z, sig = synth.static_fields(cfg)

@@ -1075,15 +1075,43 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
     for (int ly = warp; ly < Hh; ly += NT / 32) {
       float th[MAXC], gz[MAXC];
       uint32_t cd[MAXC];
+      if (VARIANT == SBD_VARIANT_GENERIC) {
+        // everything that depends on the row only is resolved once: virtual halo clamp, plane row,
+        // and whether theta of this row lives in a neighbour rank's (peer-mapped) plane
+        const int gy = y0 - R + ly;
+        int gyl = gy;
+        if ((a.g.vh & 2) && gyl < 0) gyl = 0;
+        if ((a.g.vh & 4) && gyl >= a.g.ny) gyl = a.g.ny - 1;
+        const size_t rowoff = (size_t)min(max(gyl + a.g.h, 0), a.g.ldy - 1) * a.g.ldx;
+        const float* trow = a.theta + rowoff;
+        if (gy < 0 && a.theta_up) trow = a.theta_up + (size_t)(a.ny_up + gy + a.g.h) * a.g.ldx;
+        else if (gy >= a.g.ny && a.theta_dn) trow = a.theta_dn + (size_t)(gy - a.g.ny + a.g.h) * a.g.ldx;
+        const float* grow = a.gzsm + rowoff;
+        const uint16_t* crow = a.code + rowoff;
 #pragma unroll
-      for (int cch = 0; cch < MAXC; ++cch) {
-        const int lx = cch * 32 + lane;
-        th[cch] = 0.0f; gz[cch] = 0.0f; cd[cch] = 0u;
-        if (lx < W) {
-          const int sidx = nbr_index<VARIANT>(a.g, x0 - R + lx, y0 - R + ly);
-          th[cch] = load_theta<VARIANT>(a, x0 - R + lx, y0 - R + ly, sidx);
-          gz[cch] = a.gzsm[sidx];
-          cd[cch] = a.code[sidx];
+        for (int cch = 0; cch < MAXC; ++cch) {
+          const int lx = cch * 32 + lane;
+          th[cch] = 0.0f; gz[cch] = 0.0f; cd[cch] = 0u;
+          if (lx < W) {
+            int gx = x0 - R + lx;
+            if (a.g.vh & 1) gx = (gx < 0) ? gx + a.g.nx : ((gx >= a.g.nx) ? gx - a.g.nx : gx);
+            const int x = min(max(gx + a.g.h, 0), a.g.ldx - 1);
+            th[cch] = trow[x];
+            gz[cch] = grow[x];
+            cd[cch] = crow[x];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int cch = 0; cch < MAXC; ++cch) {
+          const int lx = cch * 32 + lane;
+          th[cch] = 0.0f; gz[cch] = 0.0f; cd[cch] = 0u;
+          if (lx < W) {
+            const int sidx = nbr_index<VARIANT>(a.g, x0 - R + lx, y0 - R + ly);
+            th[cch] = a.theta[sidx];
+            gz[cch] = a.gzsm[sidx];
+            cd[cch] = a.code[sidx];
+          }
         }
       }
 #pragma unroll

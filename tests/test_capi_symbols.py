@@ -78,3 +78,28 @@ def test_f2py_mirror_argument_checks():
         seabreeze.get_edges(a, np.zeros((6, 8), np.float32))
     with pytest.raises(ValueError):
         seabreeze.get_dist(a, a, np.zeros(7), np.zeros(6))
+
+
+def test_argument_validation_status_codes():
+    """Status codes of include/sbd.h that do not need a device: 1 = bad dimensions (the UM hook's
+    `error = 1`, UM/vn10.7/sea_breeze_diag.F90:198-201), 2 = invalid argument."""
+    import ctypes as C
+    from seabreeze_param_b200 import _capi
+    lib = _capi.load()
+    h = C.c_void_p()
+    assert lib.sbd_plan_create(C.byref(h), 0, 0, 10, 5, 2, None) == 1        # nx < 1
+    assert lib.sbd_plan_create(C.byref(h), 0, 10, 10, 0, 2, None) == 1       # nz < 1
+    assert lib.sbd_plan_create(C.byref(h), 7, 10, 10, 5, 2, None) == 2       # unknown variant
+    assert lib.sbd_plan_create(C.byref(h), 0, 10, 10, 5, 0, None) == 2       # generic needs a halo
+    assert lib.sbd_plan_create(None, 0, 10, 10, 5, 2, None) == 2
+    a = np.zeros((8, 8), np.float32)
+    assert lib.sbd_get_edges_f32(a.ctypes.data, a.ctypes.data, a.ctypes.data, 4, 4, 0, 1, None) == 2   # halo < 1
+    assert lib.sbd_get_edges_f32(None, a.ctypes.data, a.ctypes.data, 4, 4, 1, 1, None) == 2
+    assert lib.sbd_py_get_dist_f32(a.ctypes.data, a.ctypes.data, a.ctypes.data, a.ctypes.data, 1, 8, 180.0,
+                                   a.ctypes.data, None) == 1                                           # nlons < 2
+    assert lib.sbd_plan_step(None, 1.0, 1, *([a.ctypes.data] * 8), None) == 2
+    assert b"" != lib.sbd_last_error()
+    p = _capi.default_params(0)
+    assert abs(p.target_plev - 70000.0) < 1e-3 and p.missing == 0.0 and abs(p.gmma + 0.0060956) < 1e-9
+    q = _capi.default_params(1)
+    assert q.missing == np.float32(2.0e20)

@@ -400,14 +400,14 @@ def main():
     abytes_step = algorithmic_bytes(n_cells, n_coastal, nz, six_frac)
     kms = statistics.mean(kern_ms)
     achieved = abytes / (kms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "sbdk::k_scan_quad (level scan over p + thresholds; timed alone.  The window kernel "
+    roofline = {"bound": "hbm", "kernel": "sbdk::k_scan_quad_regs<5,128> (level scan over p + thresholds; timed alone.  The window kernel "
                 "sbdk::k_trigger, timed alone: %.2f us; in the timed steps the two overlap)" % (1e3 * statistics.mean(win_ms)), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes, "algorithmic_bytes_per_step": abytes_step,
                 "step_achieved_gbs": abytes_step / (ms_per_step * 1e-3) / 1e9,
                 "step_frac": abytes_step / (ms_per_step * 1e-3) / 1e9 / peak, "kernel_ms": kms,
                 "kernel_ms_min": min(kern_ms), "kernel_share_of_step": kms / ms_per_step}
-    prof = os.path.join(ROOT, "profiles", "traffic_k_scan_quad.json")
+    prof = os.path.join(ROOT, "profiles", "traffic_k_scan_quad_regs.json")
     if os.path.exists(prof):
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")

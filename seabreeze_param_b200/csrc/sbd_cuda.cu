@@ -1431,6 +1431,113 @@ __global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* _
   }
 }
 
+// Register form of k_scan_quad: B levels of the quad's four columns are requested with B
+// independent 16-byte loads (asm volatile keeps them together ahead of the compares), no shared
+// memory at all.  Measured with scripts/mb_scan.cu: ~35 us for the c2 access pattern against
+// ~37-38 us for the cp.async form; in the step (c2, beside the window kernel) B = 5 is best:
+// 43.6 us per step (B=2: 57.6, 3: 46.6, 4: 45.0, 5: 43.6, 7: 44.7, 10: 46.0, 14: 47.3; cp.async form
+// 50.5) -- few registers per thread keep enough scan CTAs resident while the window kernel runs.
+// SBD_SCAN_REGS=<B> selects the batch, SBD_SCAN_REGS=0 the cp.async kernel.
+template <int B, int NT>
+__global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const int* __restrict__ quads,
+                                                       int n_quads)
+{
+  const int i = blockIdx.x * NT + threadIdx.x;
+  if (i >= n_quads) return;
+  const int m = quads[i];
+  const int c0 = m * 4;
+  const size_t n2 = (size_t)a.g.nx * a.g.ny;
+  const size_t stride4 = n2 >> 2;
+  const float tp = a.prm.target_plev;
+  const int nz = a.nz;
+  const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
+  if (a.order == 0) asm volatile("griddepcontrol.launch_dependents;");
+  uint32_t cdq[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j;
+    const int y = c / a.g.nx, x = c - y * a.g.nx;
+    cdq[j] = a.code[(size_t)(y + a.g.h) * a.g.ldx + (x + a.g.h)];
+  }
+  float4 ws4 = make_float4(0.f, 0.f, 0.f, 0.f), wd4 = ws4;
+  if (a.order == 1 && !a.first_step) {
+    ws4 = __ldcg(reinterpret_cast<const float4*>(a.ws) + m);
+    wd4 = __ldcg(reinterpret_cast<const float4*>(a.wd) + m);
+  }
+  float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+  int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+  int pf_lev = -1;
+  for (int k0 = 0; k0 < nz; k0 += B) {
+    float4 d[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int kk = min(k0 + j, nz - 1);
+      asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(d[j].x), "=f"(d[j].y), "=f"(d[j].z), "=f"(d[j].w)
+                   : "l"(pq + (size_t)kk * stride4));
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int kk = k0 + j;
+      if (kk < nz) {
+        const float e0 = fabsf(d[j].x - tp), e1 = fabsf(d[j].y - tp), e2 = fabsf(d[j].z - tp), e3 = fabsf(d[j].w - tp);
+        // minloc(abs(p - target_plev)): level 0 initialises, later levels need a strict < (G:223)
+        if (kk == 0 || e0 < b0) { b0 = e0; l0 = kk; }
+        if (kk == 0 || e1 < b1) { b1 = e1; l1 = kk; }
+        if (kk == 0 || e2 < b2) { b2 = e2; l2 = kk; }
+        if (kk == 0 || e3 < b3) { b3 = e3; l3 = kk; }
+      }
+    }
+    if (l0 != pf_lev) {
+      pf_lev = l0;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(a.u + (size_t)l0 * n2) + m));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(a.v + (size_t)l0 * n2) + m));
+    }
+  }
+  bool act[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) act[j] = (cdq[j] & 0x7fffu) != 0;
+  // wind at the selected levels: all loads first
+  const int lv[4] = {l0, l1, l2, l3};
+  float uu[4], vv[4];
+  if (l0 == l1 && l1 == l2 && l2 == l3) {  // the usual case: one 16-byte load each
+    const float4 u4 = __ldcs(reinterpret_cast<const float4*>(a.u + (size_t)l0 * n2) + m);
+    const float4 v4 = __ldcs(reinterpret_cast<const float4*>(a.v + (size_t)l0 * n2) + m);
+    uu[0] = u4.x; uu[1] = u4.y; uu[2] = u4.z; uu[3] = u4.w;
+    vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uu[j] = __ldcs(a.u + (size_t)lv[j] * n2 + c0 + j);
+      vv[j] = __ldcs(a.v + (size_t)lv[j] * n2 + c0 + j);
+    }
+  }
+  float nws[4], nwd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wind_from_uv(a, uu[j], vv[j], nws[j], nwd[j]);
+  if (a.order == 1) {
+    // this grid is the programmatic dependent of the window kernel: wait for its n_thc, then
+    // thresholds, scaling and state update right here (G:235-266) -- no further kernel
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.thc) + m);
+    const float thc_[4] = {thc4.x, thc4.y, thc4.z, thc4.w};
+    const float wsp[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
+    const float wdp[4] = {wd4.x, wd4.y, wd4.z, wd4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (act[j]) trigger_point_vals(a, (size_t)(c0 + j), thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
+    return;
+  }
+  if (act[0] && act[1] && act[2] && act[3]) {
+    reinterpret_cast<float4*>(a.nws)[m] = make_float4(nws[0], nws[1], nws[2], nws[3]);
+    reinterpret_cast<float4*>(a.nwd)[m] = make_float4(nwd[0], nwd[1], nwd[2], nwd[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (act[j]) { a.nws[c0 + j] = nws[j]; a.nwd[c0 + j] = nwd[j]; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4 fused step (generic variant, coarse grids): ONE launch per timestep.  A CTA owns a 64x16-cell
 // tile and splits into two roles that run side by side on the same SM:
@@ -1980,7 +2087,30 @@ int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false, int q0 = 0, int q1 =
       }
       const bool use_pdl = pdl && !p->timing;
       int rc = SBD_OK;
-      if (q1 > q0) {
+      static int use_regs = -1;
+      if (use_regs < 0) { const char* e = getenv("SBD_SCAN_REGS"); use_regs = e ? atoi(e) : 5; }
+      if (q1 > q0 && use_regs) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cdiv(q1 - q0, QNT));
+        cfg.blockDim = dim3(QNT);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = p->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const int* quads = p->d_quads + q0;
+        int nq = q1 - q0;
+        if (use_regs == 14) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<14, QNT>, (const TrigArgs)a, quads, nq));
+        else if (use_regs == 7) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<7, QNT>, (const TrigArgs)a, quads, nq));
+        else if (use_regs == 5) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<5, QNT>, (const TrigArgs)a, quads, nq));
+        else if (use_regs == 4) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<4, QNT>, (const TrigArgs)a, quads, nq));
+        else if (use_regs == 3) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<3, QNT>, (const TrigArgs)a, quads, nq));
+        else if (use_regs == 2) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<2, QNT>, (const TrigArgs)a, quads, nq));
+        else CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<10, QNT>, (const TrigArgs)a, quads, nq));
+        LAUNCHED();
+      } else if (q1 > q0) {
         if (G == 5) rc = launch_scan_quad<5, QNT>(p, a, qsmem, use_pdl, q0, q1);
         else if (G == 7) rc = launch_scan_quad<7, QNT>(p, a, qsmem, use_pdl, q0, q1);
         else if (G == 10) rc = launch_scan_quad<10, QNT>(p, a, qsmem, use_pdl, q0, q1);

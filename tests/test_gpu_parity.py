@@ -236,6 +236,59 @@ def test_generic_seabreeze_diag_steps(oracle, name, level_scan):
     plan.close()
 
 
+@pytest.mark.parametrize("nx,ny", [(97, 63), (130, 41), (33, 35)])
+def test_generic_odd_sizes_scalar_scan(oracle, nx, ny):
+    """nx*ny not a multiple of 4 (no aligned quads): the scalar level scan + k_final path, plan and
+    one-shot, ragged tiles on both axes."""
+    cfg = synth.Config("t_odd", nx, ny, 7, 4, "generic", 3.0, False, 1440.0, "odd-size test")
+    case = generic_case(cfg, oracle)
+    plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
+    plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
+    so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    sp = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    sg = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    for step in (1, 2, 15):
+        theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
+        fo = oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"],
+                                   case["sigma_h"], *so, cfg.h)
+        fp = np.zeros((ny, nx), np.uint8)
+        plan.step(cfg.timestep, step, p, u, v, theta_h, *sp, flags=fp)
+        generic.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"], case["sigma_h"], *sg)
+        for a, b, c, nm in zip(so, sp, sg, ("windspeed", "winddir", "thc", "sb_con")):
+            assert_bits_equal(a, b, "plan %s step %d" % (nm, step))
+            assert_bits_equal(a, c, "one-shot %s step %d" % (nm, step))
+        assert np.array_equal(fo, fp)
+    plan.close()
+
+
+def test_generic_split_api_matches_single_call(oracle):
+    """sbd_plan_step_scan + sbd_plan_step_finish (scan -> window -> final, the multi-GPU order) gives
+    the same bits as sbd_plan_step (window -> scan + thresholds)."""
+    import torch
+    cfg = synth.CONFIGS["t_gen"]
+    case = generic_case(cfg, oracle)
+    ny, nx = cfg.ny, cfg.nx
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    plans = [generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h) for _ in range(2)]
+    for pl in plans:
+        pl.set_static(t(case["mask_h"]), t(case["z_h"]), t(case["sigma_h"]))
+    st = [[torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(4)] for _ in range(2)]
+    so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    for step in (1, 2, 15):
+        theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
+        oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"], case["sigma_h"], *so, cfg.h)
+        dp, du, dv, dth = t(p), t(u), t(v), t(theta_h)
+        plans[0].step(cfg.timestep, step, dp, du, dv, dth, *st[0])
+        plans[1].step_scan(dp, du, dv)
+        plans[1].step_finish(cfg.timestep, step, dth, *st[1])
+        for pl in plans:
+            pl.sync()
+        for a, b, c, nm in zip(so, st[0], st[1], ("windspeed", "winddir", "thc", "sb_con")):
+            assert_bits_equal(a, b.cpu().numpy(), "single %s step %d" % (nm, step))
+            assert_bits_equal(a, c.cpu().numpy(), "split %s step %d" % (nm, step))
+
+
 def test_generic_virtual_halo(oracle):
     """Plan halo mode 7: swap_bounds folded into the kernels' reads -- theta arrives with garbage in
     its halo and the result equals the run with explicitly filled halos."""

@@ -382,8 +382,8 @@ def main():
         d2h = 4 * (4 * n_cells) + n_cells
         e2e = {"value": world * n_cells * ne / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": ne, "ms_per_step": 1e3 * dt / ne,
-               "api": "Plan.step with numpy arrays in pinned host memory (blocking call); p: DMA of the northern "
-                      "rows + zero-copy gather of the southern columns",
+               "api": "Plan.step with numpy arrays in pinned host memory (blocking call); p: DMA of the rows that "
+                      "hold coastal-zone cells (up to the split row) + zero-copy gather of the columns south of it",
                "host_input_bytes_per_step": 4 * (3 * n_cells * nz + (nx + 2 * h) * (ny + 2 * h) + 3 * n_cells)}
 
     if rank != 0:

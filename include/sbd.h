@@ -193,9 +193,10 @@ int sbd_plan_info(sbd_plan* plan, int* nn_max, int* n_coastal, float* stats4);
 /* Number of aligned 4-cell groups with at least one coastal-zone cell (the units the level scan
  * streams; 16 bytes per group and level).  -1 before sbd_plan_set_static. */
 int sbd_plan_n_quads(sbd_plan* plan);
-/* Host-buffer steps with pinned p use a hybrid transfer: rows [0, ysplit) of every level are copied
- * by the DMA engine while the level scan of the remaining quads gathers its columns over PCIe in
- * place.  Returns the split row and how many quads of the compacted list lie north of it. */
+/* Host-buffer steps with pinned p use a hybrid transfer: the block of rows that holds the northern
+ * quads (from the first row with a coastal-zone cell to the split row) is copied level by level by
+ * the DMA engine, while the level scan of the remaining quads gathers its columns over PCIe in
+ * place.  Returns the number of rows copied and how many quads of the compacted list they serve. */
 int sbd_plan_host_split(sbd_plan* plan, int* ysplit, int* n_quads_north);
 /* One timestep, generic variant (G:170-269 after G:166-167). */
 int sbd_plan_step(sbd_plan* plan, float timestep, int timestep_number, const float* p, const float* u,

@@ -30,9 +30,10 @@ plan.set_stream(stream.cuda_stream)
 plan.set_static(mk, zh, sh)
 print(plan.info())
 flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+flags = torch.zeros((ny, nx), dtype=torch.uint8, device=dev) if os.environ.get("PROBE_FLAGS") else None
 def step(k):
     th, p, u, v = dsteps[k % len(dsteps)]
-    plan.step(cfg.timestep, k + 2, p, u, v, th, *state)
+    plan.step(cfg.timestep, k + 2, p, u, v, th, *state, flags=flags)
 for k in range(5): step(k)
 torch.cuda.synchronize()
 t0 = time.perf_counter()

@@ -1861,7 +1861,7 @@ struct sbd_plan {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t e_copy = nullptr, e_main = nullptr;
   float* d_pfull = nullptr;
-  int ysplit = 0, n_quads_top = 0;
+  int ysplit = 0, yfirst = 0, n_quads_top = 0;
   const float *peer_up = nullptr, *peer_dn = nullptr;  // neighbour ranks' theta planes (peer-mapped)
   int peer_ny_up = 0;
   const float *cur_p = nullptr, *cur_u = nullptr, *cur_v = nullptr;
@@ -2477,6 +2477,12 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
       p->n_quads_top = (int)(std::lower_bound(hq.begin(), hq.end(), (int)lim) - hq.begin());
       p->ysplit = (int)((lim * 4) / p->nx);                      // rows fully covered by quads [0, n_quads_top)
       if (((lim * 4) % p->nx) != 0) p->ysplit += 1;              // the split quad's row is copied too
+      // rows north of the first quad hold no coastal-zone cell at all: they are never read
+      p->yfirst = (p->n_quads_top > 0) ? (int)(((long long)hq[0] * 4) / p->nx) : 0;
+      if (p->n_quads_top > 0) {
+        const int ylast = (int)(((long long)hq[p->n_quads_top - 1] * 4 + 3) / p->nx);  // last row a northern quad touches
+        p->ysplit = min(p->ysplit, ylast + 1);
+      }
     }
   }
   return SBD_OK;
@@ -2514,7 +2520,7 @@ int sbd_plan_n_quads(sbd_plan* p) { return (p && p->have_static) ? p->n_quads : 
 int sbd_plan_host_split(sbd_plan* p, int* ysplit, int* n_quads_north)
 {
   if (!p || !p->have_static) return fail(SBD_EINVAL, "plan has no static fields yet");
-  if (ysplit) *ysplit = p->ysplit;
+  if (ysplit) *ysplit = p->ysplit - p->yfirst;   // rows that travel by DMA
   if (n_quads_north) *n_quads_north = p->n_quads_top;
   return SBD_OK;
 }
@@ -2657,8 +2663,10 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
     }
     CK(cudaEventRecord(p->e_main, p->stream));            // previous users of d_pfull are done
     CK(cudaStreamWaitEvent(p->copy_stream, p->e_main, 0));
-    CK(cudaMemcpy2DAsync(p->d_pfull, n2 * sizeof(float), pp, n2 * sizeof(float),
-                         (size_t)p->ysplit * p->nx * sizeof(float), p->nz, cudaMemcpyHostToDevice, p->copy_stream));
+    CK(cudaMemcpy2DAsync(p->d_pfull + (size_t)p->yfirst * p->nx, n2 * sizeof(float),
+                         pp + (size_t)p->yfirst * p->nx, n2 * sizeof(float),
+                         (size_t)(p->ysplit - p->yfirst) * p->nx * sizeof(float), p->nz, cudaMemcpyHostToDevice,
+                         p->copy_stream));
     CK(cudaEventRecord(p->e_copy, p->copy_stream));
     if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
     if ((rc = launch_scan(p, a, true, p->n_quads_top, p->n_quads))) return rc;   // south: zero-copy

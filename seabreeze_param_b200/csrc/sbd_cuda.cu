@@ -945,6 +945,57 @@ __device__ __forceinline__ void window_fixed(const float* __restrict__ s_t0, con
   }
 }
 
+// Warp-uniform form of the window sum for the patch-raster order (km-scale grids): all 32 lanes of
+// a warp (an 8x4 patch of cells) walk the window of the LARGEST radius in the warp, nn_w, with
+// identical loop bounds; each lane masks the elements outside its own (2nn+1)^2 window.  No
+// divergent loops, and at every step the lanes read the patch-shaped, conflict-free set of
+// shared-memory words.  The per-lane sequence of additions is still the reference's raster order
+// over the lane's own window (masked elements are simply not added).
+__device__ __forceinline__ void window_patch_uniform(const float* __restrict__ s_t0,
+                                                     const uint32_t* __restrict__ s_bits, int W, int WBITS, int lcx,
+                                                     int lcy, int nn, int nn_w, bool active, float& T_l, float& T_s,
+                                                     uint32_t& c_l)
+{
+  const int lo = nn_w - nn, hi = nn_w + nn;  // this lane's columns inside the warp-wide row segment
+  const int wlen = 2 * nn_w + 1;
+  for (int dy = -nn_w; dy <= nn_w; ++dy) {
+    const bool rowin = active && dy >= -nn && dy <= nn;
+    const int ii = lcy + dy;
+    int bpos = ii * WBITS + lcx - nn_w;
+    const float* tp = s_t0 + ii * W + lcx - nn_w;
+    int cb = 0;
+    while (cb < wlen) {
+      const int cnt = min(wlen - cb, 32);
+      const uint32_t bits = __funnelshift_r(s_bits[bpos >> 5], s_bits[(bpos >> 5) + 1], bpos & 31);
+      // lane's window restricted to this chunk: bits [lo-cb, hi-cb] clipped to [0, cnt)
+      uint32_t win = 0u;
+      if (rowin) {
+        const int a0 = max(lo - cb, 0), a1 = min(hi - cb, cnt - 1);
+        if (a1 >= a0) win = (0xffffffffu >> (31 - (a1 - a0))) << a0;
+      }
+      uint32_t L = bits & win, S = ~bits & win;
+      c_l += __popc(L);
+      int j = 0;
+      for (; j + 8 <= cnt; j += 8) {
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu) {
+          const float t = tp[j + uu];
+          if (L & (1u << uu)) T_l = T_l + t;   // G:200-202
+          if (S & (1u << uu)) T_s = T_s + t;   // G:204-205
+        }
+        L >>= 8; S >>= 8;
+      }
+      for (; j < cnt; ++j) {
+        const float t = tp[j];
+        if (L & 1u) T_l = T_l + t;
+        if (S & 1u) T_s = T_s + t;
+        L >>= 1; S >>= 1;
+      }
+      bpos += cnt; tp += cnt; cb += cnt;
+    }
+  }
+}
+
 // n_thc of one coastal-zone cell of a staged tile: sequential raster sum over its final (2nn+1)^2
 // window, bit-identical to the last pass of the reference's growing search (G:191-214), then G:216.
 // ent = land << 31 | bucket << 16 | local id (bucket NB-1: wider than the tile halo -> global path).
@@ -1025,7 +1076,7 @@ __device__ __forceinline__ float cell_thc(const TrigArgs& a, const float* __rest
 //   SPLIT (generic): n_thc is stored to thc[] (state update G:262); level search + thresholds
 //            run in k_scan_quad / k_final.  Otherwise (python: one global level) the thresholds
 //            are applied here.
-template <int VARIANT, int TX, int TY, int NT, int RMAX, bool SPLIT>
+template <int VARIANT, int TX, int TY, int NT, int RMAX, bool SPLIT, bool PATCH = (RMAX > 16)>
 __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(const TrigArgs a)
 {
   constexpr int CPT = TX * TY / NT;  // cells per thread in phase 2
@@ -1034,12 +1085,19 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
   // sum windows of equal size.  Large radii (km-scale grids, RMAX > 16): plain raster order -- nn is
   // 1-Lipschitz in space, so neighbouring lanes have nearly equal windows anyway, and consecutive
   // lanes then read consecutive shared-memory words (no bank conflicts).
-  constexpr bool RASTER = false;  // measured on c3: raster 12.7 ms vs bucketed 10.9 ms (lane divergence outweighs the bank conflicts)
+  //   measured on c3 (4000x3000, nn up to 54): bucketed 10.9 ms (LDS bank conflicts: lanes sit at
+  //   scattered tile positions), plain raster rows 12.7 ms (a warp spans 32 cells of one row, nn varies
+  //   too much).  Used instead: raster over 8x4-cell PATCHES -- compact in both directions, so nn
+  //   within a warp differs by a few cells at most, and with a row pitch == 8 (mod 32) words the 32
+  //   lanes of a patch hit 32 different banks.
+  constexpr bool RASTER = PATCH;
   static_assert(TX % 32 == 0 && NT % TX == 0 && (TX * TY) % NT == 0 && TX * TY <= 65536 && RMAX < 63, "tile shape");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int R = a.R;
   const int W = TX + 2 * R, Hh = TY + 2 * R;
-  const int total = W * Hh;
+  // row pitch of the t0 tile in words; patch-raster mode pads it to == 8 (mod 32)
+  const int WP = RASTER ? (W + ((8 - (W & 31)) & 31)) : W;
+  const int total = WP * Hh;
   const int WBW = (W + 31) >> 5, WBITS = WBW * 32;  // land bits: rows padded to whole words
   float* s_t0 = reinterpret_cast<float*>(smem_raw);
   // land/sea sign of every staged cell (bit ly*WBITS + lx), two pad words at the end so that the
@@ -1117,7 +1175,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
 #pragma unroll
       for (int cch = 0; cch < MAXC; ++cch) {
         const int lx = cch * 32 + lane;
-        if (lx < W) s_t0[ly * W + lx] = th[cch] - gz[cch];  // G:167
+        if (lx < W) s_t0[ly * WP + lx] = th[cch] - gz[cch];  // G:167
         const uint32_t bb = __ballot_sync(0xffffffffu, (cd[cch] >> 15) != 0);
         if (lane == 0 && cch * 32 < WBITS) s_bits[ly * WBW + cch] = bb;
       }
@@ -1193,13 +1251,47 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
 
   // ---- phase 3 ----
   for (int e = tid; e < n_list; e += NT) {
-    const uint32_t ent = s_list[e];
-    if (RASTER && ((ent >> 16) & 0x7fffu) == 0) continue;
-    const int lid = (int)(ent & 0xffffu);
-    const int ly = lid / TX, lx = lid - ly * TX;
-    const int gx = x0 + lx, gy = y0 + ly;
-    const int so = own_index<VARIANT>(a.g, gx, gy);
-    const float n_thc = cell_thc<VARIANT, NB>(a, s_t0, s_bits, W, WBITS, R, ent, lx, ly, gx, gy, so);
+    uint32_t ent;
+    float n_thc;
+    int lid, lx, ly, gx, gy, so;
+    if (RASTER) {
+      // e -> cell of an 8x4 patch: lanes 0..7 along x, 4 rows per warp; all lanes stay together
+      const int patch = e >> 5, l = e & 31;
+      const int px = patch % (TX / 8), py = patch / (TX / 8);
+      ly = py * 4 + (l >> 3); lx = px * 8 + (l & 7);
+      lid = ly * TX + lx;
+      ent = s_list[lid];
+      gx = x0 + lx; gy = y0 + ly;
+      const int bkt = (int)((ent >> 16) & 0x7fffu);
+      const bool act = bkt != 0;
+      const bool in_tile = act && bkt != NB - 1;
+      const int nn_w = __reduce_max_sync(0xffffffffu, in_tile ? bkt : 0);
+      float T_l = 0.0f, T_s = 0.0f;
+      uint32_t c_l = 0, c_s = 0;
+      int nn = bkt;
+      if (nn_w > 0)
+        window_patch_uniform(s_t0, s_bits, WP, WBITS, R + lx, R + ly, in_tile ? bkt : 0, nn_w, in_tile, T_l, T_s, c_l);
+      if (!act) continue;
+      so = own_index<VARIANT>(a.g, gx, gy);
+      if (in_tile) {
+        const int wl = 2 * nn + 1;
+        c_s = (uint32_t)(wl * wl) - c_l;
+      } else {
+        nn = (int)(a.code[so] & 0x7fffu);
+        T_l = 0.0f; T_s = 0.0f; c_l = 0; c_s = 0;
+        window_sums_global<VARIANT>(a, gx, gy, nn, T_l, T_s, c_l, c_s);
+      }
+      const float n_l = (float)min(c_l, 16777216u), n_s = (float)min(c_s, 16777216u);
+      const float mul = (ent >> 31) ? 1.0f : -1.0f;             // G:182-186
+      n_thc = mul * ((T_l / n_l) - (T_s / n_s));                // G:216
+    } else {
+      ent = s_list[e];
+      lid = (int)(ent & 0xffffu);
+      ly = lid / TX; lx = lid - ly * TX;
+      gx = x0 + lx; gy = y0 + ly;
+      so = own_index<VARIANT>(a.g, gx, gy);
+      n_thc = cell_thc<VARIANT, NB>(a, s_t0, s_bits, WP, WBITS, R, ent, lx, ly, gx, gy, so);
+    }
     const size_t c = (size_t)gy * a.g.nx + gx;
     if (SPLIT) {
       // generic: n_thc goes straight into the caller's thc array (state update G:262); the
@@ -2128,14 +2220,16 @@ int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false, int q0 = 0, int q1 =
 }
 
 // one tile shape of the window kernel (see launch_trigger)
-template <int VARIANT, int TX, int TY, int NT, int RMAX>
+template <int VARIANT, int TX, int TY, int NT, int RMAX, bool PATCH = (RMAX > 16)>
 int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
 {
   constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
   const int R = a.R;
-  const size_t cells = (size_t)(TX + 2 * R) * (TY + 2 * R);
+  const int W = TX + 2 * R;
+  const int WP = PATCH ? (W + ((8 - (W & 31)) & 31)) : W;   // see k_trigger: patch-raster row pitch
+  const size_t cells = (size_t)WP * (TY + 2 * R);
   const size_t smem = cells * 4 + ((size_t)(TY + 2 * R) * ((TX + 2 * R + 31) / 32) + 2) * 4 + (size_t)TX * TY * 4;
-  auto kern = k_trigger<VARIANT, TX, TY, NT, RMAX, GEN>;
+  auto kern = k_trigger<VARIANT, TX, TY, NT, RMAX, GEN, PATCH>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
   a.nws = p->d_nws;
@@ -2192,7 +2286,12 @@ int launch_trigger(sbd_plan* p, TrigArgs& a)
       default: return launch_trigger_cfg<VARIANT, 64, 16, 256, 16>(p, a);
     }
   }
-  return launch_trigger_cfg<VARIANT, 128, 64, 1024, 56>(p, a);
+  static int patch = -1;
+  if (patch < 0) { const char* e = getenv("SBD_PATCH"); patch = e ? atoi(e) : 1; }
+  if (patch == 0) return launch_trigger_cfg<VARIANT, 128, 64, 1024, 56, false>(p, a);
+  if (patch == 2) return launch_trigger_cfg<VARIANT, 64, 64, 512, 56, true>(p, a);
+  if (patch == 3) return launch_trigger_cfg<VARIANT, 64, 32, 256, 56, true>(p, a);
+  return launch_trigger_cfg<VARIANT, 128, 64, 1024, 56, true>(p, a);
 }
 
 int ensure_device()

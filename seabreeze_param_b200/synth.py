@@ -43,6 +43,8 @@ CONFIGS = {
                  "global 0.1 degree grid 3600x1800, 37 pressure levels, 24 hourly records"),
     "c5": Config("c5", 480, 241, 37, 0, "python", 4.0, False, 360.0,
                  "ERA-Interim-like 0.75 degree grid 480x241, 37 levels (python_wrapper/run.conf:5)"),
+    "c3s": Config("c3s", 1000, 752, 4, 54, "generic", 40.0, True, 1440.0,
+                  "probe: 1/16 of the regional 2.5 km domain (same mask statistics as c3), 4 levels"),
     # small cases for unit tests
     "t_gen": Config("t_gen", 96, 64, 12, 5, "generic", 4.0, False, 1440.0, "test: small generic grid"),
     "t_py": Config("t_py", 360, 181, 9, 0, "python", 4.0, False, 360.0, "test: small python-variant grid"),

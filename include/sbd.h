@@ -180,6 +180,24 @@ int sbd_plan_set_halo_mode(sbd_plan* plan, int mode);
  * interior rows; NULL = that side's halo comes from this plane (or the halo mode).  ny_up = interior
  * rows of the northern neighbour.  The pointers stay in force until changed. */
 int sbd_plan_set_peer_theta(sbd_plan* plan, const float* theta_up, int ny_up, const float* theta_dn);
+/* Per-step synchronisation of the neighbour reads above without a separate barrier launch.
+ * sync_local: >= 4 zero-initialised uint32 words in this rank's device memory that the neighbours
+ * can write (peer / symmetric memory); sync_up / sync_dn: the same array of the northern / southern
+ * neighbour as mapped into this process (NULL where there is no neighbour).  Every step the window
+ * kernel posts its step sequence number into the neighbours' words and only the CTAs that read
+ * neighbour rows wait for the neighbours' own post.  Every rank must issue the same number of
+ * steps; a rank's theta plane of step k must stay untouched until its step k+1 has completed
+ * (keep at least two theta planes and alternate).  A neighbour that never posts is reported in
+ * sync_local[2], [3] after ~4 s instead of hanging the GPU.  NULL sync_local switches it off. */
+int sbd_plan_set_peer_sync(sbd_plan* plan, uint32_t* sync_local, uint32_t* sync_up, uint32_t* sync_dn);
+/* Pipelined steps for device-resident time loops (batched records, benchmarks): the window kernel
+ * of step k+1 is launched as the programmatic dependent of step k's level scan and runs under it;
+ * level scans of consecutive steps then follow each other without a gap.  Contract: the inputs of
+ * a step (p, u, v, theta and, for the first step, the state arrays) must already be complete on
+ * the device when the PREVIOUS sbd_plan_step call is issued, i.e. they must not be produced by
+ * work enqueued between two step calls.  Results are bit-identical to the unpipelined step.
+ * Steps with host pointers or with per-kernel timing enabled run unpipelined. */
+int sbd_plan_set_pipelined(sbd_plan* plan, int on);
 /* Static fields: mask = signed coast distance, z, sigma (generic: halo'd; python: nlons x nlats).
  * Computes the sigmoid statistics (sequential-order exact), the sea-level correction plane
  * gmma*z*sigmoid(sigma), the land/sea sign plane and every cell's final search radius nn.

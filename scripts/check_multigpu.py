@@ -46,11 +46,15 @@ if rank == 0:
     fl1 = torch.zeros((ny, nx), dtype=torch.uint8, device=dev)
     i1 = plan1.info()
     print("global stats 1-rank:", i1["mean"], i1["std2inv"], i1["r"], " chained:", stats)
-for step in (1, 2, 15):
+STEPS = list(range(1, 17))  # 15 is a 6-hourly step at dt = 1440 s
+sb_hist, inputs = [], []
+for step in STEPS:
     theta, p, u, v = synth.step_fields(cfg, step, land, z, lat, seed=3)
+    inputs.append((t(theta[r0:r1]), t(p[:, r0:r1]), t(u[:, r0:r1]), t(v[:, r0:r1])))
     th = ex.swap_bounds(haloed(t(theta[r0:r1]), nyl))
     plan.step(cfg.timestep, step, t(p[:, r0:r1]), t(u[:, r0:r1]), t(v[:, r0:r1]), th, *st, flags=fl)
     plan.sync()
+    sb_hist.append(st[3].clone())
     pl = peer.plane(0)
     pl.fill_(7.0e30)                               # halos hold junk: they must not be read
     pl[h:h + nyl, h:h + nx] = t(theta[r0:r1])
@@ -77,9 +81,43 @@ for step in (1, 2, 15):
             same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
             print("step", step, nm, "identical" if same.all() else "DIFFERENT (%d cells)" % (~same).sum())
             ok &= bool(same.all())
+# third plan: peer-memory halo reads with the post / wait words handled inside the window kernel (no
+# barrier launch) and pipelined steps; all 16 steps are enqueued back to back without a host sync
+peer_f = halo.PeerHalo(len(STEPS), nyl, nx, h, rank, world, dev)
+for i, (th_i, _, _, _) in enumerate(inputs):
+    pl = peer_f.plane(i)
+    pl.fill_(7.0e30)
+    pl[h:h + nyl, h:h + nx] = th_i
+torch.cuda.synchronize(); dist.barrier()
+plan_f = generic.Plan(SBD_VARIANT_GENERIC, nx, nyl, nz, h)
+plan_f.set_halo_mode(ex.halo_mode())
+plan_f.set_static(mk, zh, sh, stats=stats)
+plan_f.set_peer_sync(*peer_f.sync_words())
+plan_f.set_pipelined(True)
+st_f = [torch.zeros((nyl, nx), dtype=torch.float32, device=dev) for _ in range(3)]
+sb_f = [torch.zeros((nyl, nx), dtype=torch.float32, device=dev) for _ in STEPS]
+torch.cuda.synchronize()
+for i, step in enumerate(STEPS):
+    _, p_i, u_i, v_i = inputs[i]
+    plan_f.set_peer_theta(*peer_f.peers(i))
+    plan_f.step(cfg.timestep, step, p_i, u_i, v_i, peer_f.plane(i), *st_f, sb_f[i])
+plan_f.sync()
+torch.cuda.synchronize()
+if peer_f.timed_out():
+    print("rank", rank, "peer flag wait TIMED OUT"); ok = False
+def same_bits(x, y):
+    a_, b_ = x.cpu().numpy(), y.cpu().numpy()
+    return bool(((a_.view(np.uint32) == b_.view(np.uint32)) | (np.isnan(a_) & np.isnan(b_))).all())
+for i, step in enumerate(STEPS):
+    if not same_bits(sb_hist[i], sb_f[i]):
+        print("rank", rank, "step", step, "sb_con FLAG-SYNC/PIPELINED path DIFFERENT"); ok = False
+for s_a, s_b, nm in zip(st[:3], st_f, ("ws", "wd", "thc")):
+    if not same_bits(s_a, s_b):
+        print("rank", rank, nm, "final state FLAG-SYNC/PIPELINED path DIFFERENT"); ok = False
+dist.barrier()
 okt = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(okt, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("MULTIGPU_CHECK", "PASS" if int(okt.item()) else "FAIL", "world", world, "(NCCL exchange and peer-memory halo reads vs 1 rank)")
+    print("MULTIGPU_CHECK", "PASS" if int(okt.item()) else "FAIL", "world", world, "(NCCL exchange, peer-memory halo reads with barrier, and with in-kernel flags + pipelined steps, vs 1 rank)")
 dist.barrier()
 dist.destroy_process_group()

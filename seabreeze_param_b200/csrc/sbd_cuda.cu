@@ -816,7 +816,47 @@ struct TrigArgs {
   const float* theta_up; const float* theta_dn;
   int ny_up;  // interior rows of the northern neighbour's block
   int order;  // 0: scan -> window -> final (multi-GPU friendly); 1: window -> scan(+thresholds)
+  // Pipelined steps (sbd_plan_set_pipelined, order 1 only): the window kernel of step k+1 is the
+  // programmatic dependent of the level scan of step k and runs under it.  It therefore must not
+  // touch anything scan k still reads or writes: n_thc goes to one of two plan-owned scratch planes
+  // (thc_scr) and the scan's epilogue stores it into the caller's thc array (G:262).
+  int pipe;
+  float* thc_scr;
+  unsigned* pipe_ctr;  // CTAs of the window kernel that have finished (pipelined steps)
+  // Multi-GPU row blocks without a separate barrier launch: sync_local[0] / [1] are written by the
+  // northern / southern neighbour rank ("my theta plane of step sync_seq is in place"); this rank
+  // posts sync_seq into sync_up[1] and sync_dn[0].  Only CTAs that read neighbour rows wait.
+  uint32_t* sync_local; uint32_t* sync_up; uint32_t* sync_dn;
+  uint32_t sync_seq;
 };
+
+// ---- peer flags over NVLink (system scope) ----
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until the neighbour's flag has reached seq (wrap-safe); gives up after ~4 s and leaves a
+// marker in sync_local[2 + which] so that a dead peer shows up as an error instead of a hung GPU
+__device__ __forceinline__ void wait_peer_flag(uint32_t* sync_local, int which, uint32_t seq)
+{
+  const unsigned long long t0 = globaltimer_ns();
+  while ((int32_t)(ld_acquire_sys(sync_local + which) - seq) < 0) {
+    __nanosleep(64);
+    if (globaltimer_ns() - t0 > 4000000000ull) { sync_local[2 + which] = seq; break; }
+  }
+}
 
 // theta at interior-relative (gx, gy): the local plane, or -- for rows that belong to a neighbouring
 // rank whose plane is peer-mapped -- that rank's interior rows, read over NVLink.
@@ -1111,8 +1151,30 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int tid = threadIdx.x;
 
-  // order 1: the level scan follows as a programmatic dependent and may start right away
-  if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
+  // order 1: the level scan follows as a programmatic dependent and may start right away.
+  // Pipelined: this grid itself runs under the PREVIOUS step's scan; its own scan is released at
+  // the very end, once that previous scan has completed (see the end of the kernel).
+  if (SPLIT && a.order == 1 && !a.pipe) asm volatile("griddepcontrol.launch_dependents;");
+
+  if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {
+    // multi-GPU: tell the neighbours that this rank's theta of this step is in place (the plane
+    // was written by work that precedes this kernel), then -- only in CTAs that read neighbour
+    // rows (every cell reads within the halo width h) -- wait for the neighbours' own posts
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+      __threadfence_system();
+      if (a.sync_up) st_release_sys(a.sync_up + 1, a.sync_seq);
+      if (a.sync_dn) st_release_sys(a.sync_dn + 0, a.sync_seq);
+    }
+    const bool need_up = a.theta_up && (y0 - a.g.h < 0);
+    const bool need_dn = a.theta_dn && (y0 + TY + a.g.h > a.g.ny);
+    if (need_up || need_dn) {
+      if (tid == 0) {
+        if (need_up) wait_peer_flag(a.sync_local, 0, a.sync_seq);
+        if (need_dn) wait_peer_flag(a.sync_local, 1, a.sync_seq);
+      }
+      __syncthreads();
+    }
+  }
 
   if (tid < NB) s_cnt[tid] = 0;
   // ---- python: one pressure level for the whole grid (P:228), first minimum of |p - target| ----
@@ -1297,7 +1359,8 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
       // generic: n_thc goes straight into the caller's thc array (state update G:262); the
       // thresholds are applied by k_final once the level scan has delivered n_ws / n_wd.  This
       // grid never waits for the scan, so its CTAs retire while the scan is still streaming.
-      a.thc[c] = n_thc;
+      // (pipelined: the previous step's scan may still be reading thc -> scratch plane)
+      (a.pipe ? a.thc_scr : a.thc)[c] = n_thc;
     } else if (VARIANT == SBD_VARIANT_PYTHON) {
       const int lev = s_lev;
       const float uu = __ldg(a.u + (size_t)lev * n2 + c), vv = __ldg(a.v + (size_t)lev * n2 + c);
@@ -1326,6 +1389,21 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
       wind_from_uv(a, uu, vv, n_ws, n_wd);
       a.thc[c] = n_thc;
       trigger_point<VARIANT>(a, c, n2, n_thc, n_ws, n_wd, 0.0f);
+    }
+  }
+  if (SPLIT && a.pipe) {
+    // pipelined: this step's scan may start only when the previous step's scan has completed
+    // (state arrays, the other scratch plane).  CTAs just exit -- an exited CTA counts as having
+    // released the dependents, and its SM resources go to the CTAs still to come -- except the one
+    // that finishes last: it waits for the previous scan and then releases this step's scan.  So
+    // "this grid complete" implies "previous scan complete" for the dependent's own wait.
+    if (tid == 0) {
+      const unsigned n_cta = gridDim.x * gridDim.y;
+      if (atomicAdd(a.pipe_ctr, 1u) == n_cta - 1u) {
+        *a.pipe_ctr = 0u;  // the next window kernel cannot start before the release below
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+      }
     }
   }
 }
@@ -1543,7 +1621,9 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
   const float tp = a.prm.target_plev;
   const int nz = a.nz;
   const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
-  if (a.order == 0) asm volatile("griddepcontrol.launch_dependents;");
+  // order 0: the window kernel follows as a dependent.  Pipelined order 1: the NEXT step's window
+  // kernel does, and may run under this scan (it touches nothing this grid reads or writes).
+  if (a.order == 0 || a.pipe) asm volatile("griddepcontrol.launch_dependents;");
   uint32_t cdq[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -1611,13 +1691,16 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
     // this grid is the programmatic dependent of the window kernel: wait for its n_thc, then
     // thresholds, scaling and state update right here (G:235-266) -- no further kernel
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.thc) + m);
+    const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.pipe ? a.thc_scr : a.thc) + m);
     const float thc_[4] = {thc4.x, thc4.y, thc4.z, thc4.w};
     const float wsp[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
     const float wdp[4] = {wd4.x, wd4.y, wd4.z, wd4.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (act[j]) trigger_point_vals(a, (size_t)(c0 + j), thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
+      if (act[j]) {
+        if (a.pipe) a.thc[c0 + j] = thc_[j];  // state update G:262 (the window kernel wrote a scratch plane)
+        trigger_point_vals(a, (size_t)(c0 + j), thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
+      }
     return;
   }
   if (act[0] && act[1] && act[2] && act[3]) {
@@ -1956,6 +2039,12 @@ struct sbd_plan {
   int ysplit = 0, yfirst = 0, n_quads_top = 0;
   const float *peer_up = nullptr, *peer_dn = nullptr;  // neighbour ranks' theta planes (peer-mapped)
   int peer_ny_up = 0;
+  uint32_t *sync_local = nullptr, *sync_up = nullptr, *sync_dn = nullptr;  // sbd_plan_set_peer_sync
+  uint32_t sync_seq = 0;
+  bool pipelined = false;     // sbd_plan_set_pipelined
+  float* d_thc_scr[2] = {nullptr, nullptr};
+  unsigned* d_pipe_ctr = nullptr;
+  unsigned pipe_seq = 0;
   const float *cur_p = nullptr, *cur_u = nullptr, *cur_v = nullptr;
   // optional per-kernel CUDA-event timing of the step (bench.py roofline leg)
   bool timing = false;
@@ -2140,6 +2229,16 @@ int launch_scan_quad(sbd_plan* p, const TrigArgs& a, int qsmem, bool pdl, int q0
   return SBD_OK;
 }
 
+// which form of the quad scan runs: SBD_SCAN_REGS = B (levels in flight per thread, register form,
+// default 5) or 0 (cp.async form staged through shared memory)
+int scan_regs_setting()
+{
+  static int use_regs = -1;
+  if (use_regs < 0) { const char* e = getenv("SBD_SCAN_REGS"); use_regs = e ? atoi(e) : 5; }
+  return use_regs;
+}
+bool scan_uses_regs() { return scan_regs_setting() != 0; }
+
 // q0, q1: range of the compacted quad list to process (default: all of it)
 int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false, int q0 = 0, int q1 = -1)
 {
@@ -2179,8 +2278,7 @@ int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false, int q0 = 0, int q1 =
       }
       const bool use_pdl = pdl && !p->timing;
       int rc = SBD_OK;
-      static int use_regs = -1;
-      if (use_regs < 0) { const char* e = getenv("SBD_SCAN_REGS"); use_regs = e ? atoi(e) : 5; }
+      const int use_regs = scan_regs_setting();
       if (q1 > q0 && use_regs) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cdiv(q1 - q0, QNT));
@@ -2250,7 +2348,7 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = (a.order == 0 && !p->timing) ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = ((a.order == 0 || a.pipe) && !p->timing) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
@@ -2426,7 +2524,7 @@ void sbd_plan_destroy(sbd_plan* p)
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->e_copy) cudaEventDestroy(p->e_copy);
   if (p->e_main) cudaEventDestroy(p->e_main);
-  cudaFree(p->d_pfull);
+  cudaFree(p->d_pfull); cudaFree(p->d_thc_scr[0]);
   for (auto& s : p->stage) cudaFree(s.first);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
@@ -2451,6 +2549,27 @@ int sbd_plan_set_peer_theta(sbd_plan* p, const float* theta_up, int ny_up, const
   if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
   if (theta_up && ny_up < p->h) return fail(SBD_EINVAL, "northern neighbour block is thinner than the halo");
   p->peer_up = theta_up; p->peer_dn = theta_dn; p->peer_ny_up = ny_up;
+  return SBD_OK;
+}
+int sbd_plan_set_peer_sync(sbd_plan* p, uint32_t* sync_local, uint32_t* sync_up, uint32_t* sync_dn)
+{
+  if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
+  if (!sync_local && (sync_up || sync_dn)) return fail(SBD_EINVAL, "neighbour flags without local flags");
+  p->sync_local = sync_local; p->sync_up = sync_up; p->sync_dn = sync_dn;
+  p->sync_seq = 0;
+  return SBD_OK;
+}
+int sbd_plan_set_pipelined(sbd_plan* p, int on)
+{
+  if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
+  if (on && !p->d_thc_scr[0]) {
+    const size_t n2 = (size_t)p->nx * p->ny;
+    CK(cudaMalloc((void**)&p->d_thc_scr[0], 2 * n2 * sizeof(float) + 16));
+    p->d_thc_scr[1] = p->d_thc_scr[0] + n2;
+    p->d_pipe_ctr = reinterpret_cast<unsigned*>(p->d_thc_scr[0] + 2 * n2);
+    CK(cudaMemset(p->d_pipe_ctr, 0, 16));
+  }
+  p->pipelined = on != 0;
   return SBD_OK;
 }
 int sbd_plan_set_timing(sbd_plan* p, int on)
@@ -2674,6 +2793,10 @@ int sbd_plan_step_finish(sbd_plan* p, float timestep, int step, const float* the
   a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
   a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
   a.theta_up = p->peer_up; a.theta_dn = p->peer_dn; a.ny_up = p->peer_ny_up;
+  if (p->sync_local && (p->peer_up || p->peer_dn)) {  // one post / wait per step, inside the window kernel
+    a.sync_local = p->sync_local; a.sync_up = p->peer_up ? p->sync_up : nullptr;
+    a.sync_dn = p->peer_dn ? p->sync_dn : nullptr; a.sync_seq = ++p->sync_seq;
+  }
   p->scan_done = false;
   a.order = 0;
   if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
@@ -2716,6 +2839,10 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
   a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
   a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
   a.theta_up = p->peer_up; a.theta_dn = p->peer_dn; a.ny_up = p->peer_ny_up;
+  if (p->sync_local && (p->peer_up || p->peer_dn)) {  // one post / wait per step, inside the window kernel
+    a.sync_local = p->sync_local; a.sync_up = p->peer_up ? p->sync_up : nullptr;
+    a.sync_dn = p->peer_dn ? p->sync_dn : nullptr; a.sync_seq = ++p->sync_seq;
+  }
   if (!scan_vec_ok(p, a) || p->n_coastal == 0) {
     // scalar scan / no coastal cells: scan -> window -> final, in order
     a.order = 0; p->last_order = 0;
@@ -2724,6 +2851,12 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
     return flush_out(p, pend, any_host);
   }
   a.order = 1; p->last_order = 1;
+  // Pipelined steps (device-resident inputs only): see TrigArgs::pipe
+  if (p->pipelined && !any_host && pend.empty() && !p->timing && scan_uses_regs()) {
+    a.pipe = 1;
+    a.thc_scr = p->d_thc_scr[p->pipe_seq++ & 1u];
+    a.pipe_ctr = p->d_pipe_ctr;
+  }
   // Optional (SBD_FUSED=1): one fused, warp-specialised launch.  Measured on c2: 61.9 us per step
   // against 51 us for the two-kernel path below -- a CTA holds its window warps' registers until
   // its scan warps are done, which leaves only 12 streaming warps per SM -- so it is off by default.

@@ -142,6 +142,18 @@ class Plan:
         _capi.check(self.lib.sbd_plan_set_peer_theta(self._h, _capi.ptr(theta_up), int(ny_up), _capi.ptr(theta_dn)),
                     "plan_set_peer_theta")
 
+    def set_peer_sync(self, sync_local, sync_up, sync_dn):
+        """In-kernel post/wait flags for the neighbour reads (int32 tensors / addresses in peer-mapped
+        memory, or None); replaces a barrier launch per step.  See sbd_plan_set_peer_sync."""
+        q = _capi.ptr
+        _capi.check(self.lib.sbd_plan_set_peer_sync(self._h, q(sync_local), q(sync_up), q(sync_dn)),
+                    "plan_set_peer_sync")
+
+    def set_pipelined(self, on=True):
+        """Overlap consecutive device-resident steps (inputs of a step must be complete before the
+        previous step call is issued).  See sbd_plan_set_pipelined."""
+        _capi.check(self.lib.sbd_plan_set_pipelined(self._h, 1 if on else 0), "plan_set_pipelined")
+
     def use_own_stream(self):
         _capi.check(self.lib.sbd_plan_use_own_stream(self._h), "plan_use_own_stream")
 

@@ -133,7 +133,9 @@ class PeerHalo:
     memory (torch.distributed._symmetric_memory: peer-mapped allocations over NVLink / NVSwitch),
     and the window kernel of a neighbour reads the rows it needs straight from them
     (Plan.set_peer_theta).  What is left per step is a device-side barrier over the symmetric
-    memory's signal pads ("my theta for this step is in place / I am done reading yours")."""
+    memory's signal pads ("my theta for this step is in place / I am done reading yours"), or --
+    cheaper -- the post / wait words of sync_words() handled inside the window kernel itself
+    (Plan.set_peer_sync): no launch, and only the CTAs that touch neighbour rows ever wait."""
 
     def __init__(self, nbuf, ny_local, nx, h, rank, world, device, group=None):
         import torch
@@ -149,6 +151,24 @@ class PeerHalo:
         plane_bytes = 4 * shape[1] * shape[2]
         self._peers = [(self.up.data_ptr() + i * plane_bytes if self.up is not None else None, ny_local,
                         self.dn.data_ptr() + i * plane_bytes if self.dn is not None else None) for i in range(nbuf)]
+
+        # in-kernel post / wait words (Plan.set_peer_sync): [0] written by the northern neighbour,
+        # [1] by the southern one, [2], [3] time-out markers
+        self.flags = symm.empty((16,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.fhdl = symm.rendezvous(self.flags, group if group is not None else dist.group.WORLD)
+        self.flags_up = self.fhdl.get_buffer(rank - 1, (16,), torch.int32) if rank > 0 else None
+        self.flags_dn = self.fhdl.get_buffer(rank + 1, (16,), torch.int32) if rank < world - 1 else None
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # everybody's words are zero before anybody posts
+
+    def sync_words(self):
+        """(local, northern neighbour's, southern neighbour's) flag arrays for Plan.set_peer_sync"""
+        return self.flags, self.flags_up, self.flags_dn
+
+    def timed_out(self):
+        """True if a window kernel gave up waiting for a neighbour's post (sbd.h: sync_local[2], [3])."""
+        return bool((self.flags[2:4] != 0).any().item())
 
     def plane(self, i):
         return self.buf[i]

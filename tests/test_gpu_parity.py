@@ -289,6 +289,45 @@ def test_generic_split_api_matches_single_call(oracle):
             assert_bits_equal(a, c.cpu().numpy(), "split %s step %d" % (nm, step))
 
 
+@pytest.mark.parametrize("name", ["t_gen", "c1"])
+def test_generic_pipelined_steps(oracle, name):
+    """sbd_plan_set_pipelined: the window kernel of step k+1 runs under the level scan of step k
+    (n_thc through a double-buffered scratch plane).  12 steps enqueued back to back on preloaded
+    inputs, no host synchronisation in between: every step's sb_con / flags and the final state
+    equal the oracle's bits."""
+    import torch
+    cfg = synth.CONFIGS[name]
+    case = generic_case(cfg, oracle)
+    ny, nx = cfg.ny, cfg.nx
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    steps = list(range(1, 13)) + [15, 16]
+    so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    ref_sb, ref_fl, dins = [], [], []
+    for step in steps:
+        theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
+        fo = oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"], case["sigma_h"], *so, cfg.h)
+        ref_sb.append(so[3].copy()); ref_fl.append(np.array(fo).copy())
+        dins.append((t(p), t(u), t(v), t(theta_h)))
+    plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
+    plan.set_static(t(case["mask_h"]), t(case["z_h"]), t(case["sigma_h"]))
+    plan.set_pipelined(True)
+    st = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(3)]
+    sbs = [torch.full((ny, nx), -7.0, dtype=torch.float32, device=dev) for _ in steps]
+    fls = [torch.full((ny, nx), 9, dtype=torch.uint8, device=dev) for _ in steps]
+    torch.cuda.synchronize()
+    for i, step in enumerate(steps):
+        dp, du, dv, dth = dins[i]
+        plan.step(cfg.timestep, step, dp, du, dv, dth, *st, sbs[i], flags=fls[i])
+    plan.sync()
+    for i, step in enumerate(steps):
+        assert_bits_equal(ref_sb[i], sbs[i].cpu().numpy(), "sb_con step %d" % step)
+        assert np.array_equal(ref_fl[i], fls[i].cpu().numpy()), "flags step %d" % step
+    for a, b, nm in zip(so[:3], st, ("windspeed", "winddir", "thc")):
+        assert_bits_equal(a, b.cpu().numpy(), "final " + nm)
+    plan.close()
+
+
 def test_generic_virtual_halo(oracle):
     """Plan halo mode 7: swap_bounds folded into the kernels' reads -- theta arrives with garbage in
     its halo and the result equals the run with explicitly filled halos."""

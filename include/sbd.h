@@ -198,6 +198,13 @@ int sbd_plan_set_peer_sync(sbd_plan* plan, uint32_t* sync_local, uint32_t* sync_
  * work enqueued between two step calls.  Results are bit-identical to the unpipelined step.
  * Steps with host pointers or with per-kernel timing enabled run unpipelined. */
 int sbd_plan_set_pipelined(sbd_plan* plan, int on);
+/* Form of the window-sum kernel: 0 = automatic (strip kernel when the largest search radius is
+ * >= 9 cells, tile kernel below), 1 = tile kernel (one cell per thread, cells bucketed by radius),
+ * 2 = strip kernel (four cells per thread share every shared-memory load, packed fp32 adds).
+ * Both evaluate each cell's sums in the reference's raster order: identical bits. */
+int sbd_plan_set_window_kernel(sbd_plan* plan, int mode);
+/* Process-wide default for plans left at mode 0 (also used by the one-shot entry points). */
+int sbd_set_window_kernel_default(int mode);
 /* Static fields: mask = signed coast distance, z, sigma (generic: halo'd; python: nlons x nlats).
  * Computes the sigmoid statistics (sequential-order exact), the sea-level correction plane
  * gmma*z*sigmoid(sigma), the land/sea sign plane and every cell's final search radius nn.

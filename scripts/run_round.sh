@@ -1,8 +1,5 @@
-P="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $P scripts/check_multigpu.py > gpurun_out/mg2.log 2>&1; echo "rc=$?" >> gpurun_out/mg2.log
-timeout 300 $P bench.py --gpus 2 --no-cpu-baseline --no-e2e > gpurun_out/bench_n2_flags.json 2> gpurun_out/bench_n2.err
-BENCH_PEER_SYNC=barrier timeout 300 $P bench.py --gpus 2 --no-cpu-baseline --no-e2e > gpurun_out/bench_n2_barrier.json 2>> gpurun_out/bench_n2.err
-timeout 300 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/bench_n1_b.json 2>> gpurun_out/bench_n2.err
-grep -E "MULTIGPU|DIFFERENT|TIMED|rc=|Error|error" gpurun_out/mg2.log | head; for f in bench_n2_flags bench_n2_barrier bench_n1_b; do python -c "
-import json,sys
-d=json.load(open('gpurun_out/$f.json')); print('$f', d['ms_per_step'], d['value'])"; done; tail -5 gpurun_out/bench_n2.err
+python -m pytest tests -m gpu -x -q -k "wide or mid_radius or time_loop or seabreeze_diag_steps or golden" 2>&1 | tail -3 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log
+timeout 300 python scripts/probe_py.py c4 3 > gpurun_out/probe_c4.log 2>&1; grep -E "us/step|checksum" gpurun_out/probe_c4.log
+timeout 300 python scripts/probe_step.py c3 2>&1 | grep -E "wall|per-kernel" | cut -c1-160 > gpurun_out/probe_c3_strip.log
+cat gpurun_out/probe_c3_strip.log

@@ -782,6 +782,23 @@ __global__ void k_static_code(const float* __restrict__ mask, uint16_t* __restri
   code[s] = (uint16_t)c;
 }
 
+// Static by-product of the search radius: the number of land cells (mask >= 0, "far" cells included)
+// in every coastal-zone cell's final (2nn+1)^2 window, i.e. the reference's counter n_l after its
+// last pass (G:200-203); n_s = (2nn+1)^2 - n_l.  One thread per interior cell, same index map as the
+// window sums.  Lets the strip window kernel (k_win4) run without a land-bit plane in shared memory.
+template <int VARIANT>
+__global__ void k_static_counts(const uint16_t* __restrict__ code, uint32_t* __restrict__ cl, Geo g)
+{
+  const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y;
+  if (gx >= g.nx) return;
+  const int nn = (int)(code[own_index<VARIANT>(g, gx, gy)] & 0x7fffu);
+  uint32_t n = 0;
+  if (nn > 0)
+    for (int ii = gy - nn; ii <= gy + nn; ++ii)
+      for (int jj = gx - nn; jj <= gx + nn; ++jj) n += code[nbr_index<VARIANT>(g, jj, ii)] >> 15;
+  cl[(size_t)gy * g.nx + gx] = n;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4 trigger: fused per-step kernel.
 //   tile (TX x TY interior cells) + halo R of t0 = theta - gzsm and the land bit -> shared memory;
@@ -799,6 +816,7 @@ struct TrigArgs {
   const float* theta;    // neighbour-read plane
   const float* gzsm;     // neighbour-read plane (static)
   const uint16_t* code;  // neighbour-read plane (static)
+  const uint32_t* cl;    // land cells in each coastal-zone cell's final window (static, nx x ny)
   const float* p;        // generic: nx*ny*nz ; python: nz
   const float* u;
   const float* v;
@@ -1401,6 +1419,410 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
       const unsigned n_cta = gridDim.x * gridDim.y;
       if (atomicAdd(a.pipe_ctr, 1u) == n_cta - 1u) {
         *a.pipe_ctr = 0u;  // the next window kernel cannot start before the release below
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a', strip form of the window kernel for search radii beyond a few cells (0.1-degree and
+// km-scale grids: nn up to 18 / 55).  What changes against k_trigger:
+//   * the tile holds (t_land, t_sea) PAIRS per staged cell -- t0 in the slot of the cell's own class,
+//     0.0 in the other -- so one packed add (add.rn.f32x2 -> FADD2) advances both of the reference's
+//     running sums T_l, T_s (G:200-205) with no land/sea predicate: x + 0.0 == x exactly, and a sum
+//     that starts at +0.0 never becomes -0.0 in round-to-nearest, so the bits are the reference's;
+//   * the land / sea COUNTS of the final window are static (k_static_counts), no bit plane;
+//   * a thread owns a STRIP of 4 horizontally adjacent cells and walks the union of their windows
+//     once: every 8-byte shared-memory load feeds four independent accumulator pairs, each still
+//     adding its own window's elements in the reference's raster order.  The search radius is
+//     1-Lipschitz in space, so the radii of a strip's coastal cells differ by at most 3: all columns
+//     except 6 on either side of the walked row are inside all four windows (no per-element mask),
+//     and rows are switched per cell by a predicate that is constant along the row;
+//   * strips are bucketed by their largest radius (descending, so the longest walks start first and
+//     the lanes of a warp have equal trip counts); strips with small radii or a single coastal cell
+//     hand their cells to a one-cell-per-thread path with compile-time window sizes.
+// Tile 64 x 32 cells + halo R <= 56, row pitch == 1 (mod 16) pairs.  512 threads.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long add2(unsigned long long acc, unsigned long long v)
+{
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(v));
+  return acc;
+}
+// the same add, executed only where flag != 0 (the predicate lives inside the asm block so that the
+// accumulator stays in place: a C-level "if" around add2 makes the compiler copy the pair around)
+__device__ __forceinline__ void add2_if(unsigned long long& acc, unsigned long long v, uint32_t flag)
+{
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.rn.f32x2 %0, %0, %1;\n\t}" : "+l"(acc) : "l"(v), "r"(flag));
+}
+__device__ __forceinline__ void unpack2(unsigned long long acc, float& lo, float& hi)
+{
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+
+// one cell, compile-time radius: (2NN+1)^2 x (LDS.64 + FADD2)
+template <int NN>
+__device__ __forceinline__ unsigned long long window_fixed2(const unsigned long long* __restrict__ s_t, int WP,
+                                                            int lcx, int lcy)
+{
+  constexpr int WL = 2 * NN + 1;
+  unsigned long long acc = 0ull;
+#pragma unroll 1
+  for (int r = 0; r < WL; ++r) {
+    const unsigned long long* rp = s_t + (lcy - NN + r) * WP + lcx - NN;
+#pragma unroll
+    for (int j = 0; j < WL; ++j) acc = add2(acc, rp[j]);
+  }
+  return acc;
+}
+
+// everything after the window sums of one coastal-zone cell: n_thc (G:216), then -- depending on
+// the variant -- the state store, or the level search / wind / thresholds (as in k_trigger)
+template <int VARIANT, bool SPLIT>
+__device__ __forceinline__ void finish_cell(const TrigArgs& a, int gx, int gy, bool land_c, float T_l, float T_s,
+                                            uint32_t c_l, uint32_t c_s, int s_lev)
+{
+  const size_t n2 = (size_t)a.g.nx * a.g.ny;
+  const size_t c = (size_t)gy * a.g.nx + gx;
+  // n_l, n_s are fp32 counters in the reference: n = n + 1 saturates at 2^24
+  const float n_l = (float)min(c_l, 16777216u), n_s = (float)min(c_s, 16777216u);
+  const float mul = land_c ? 1.0f : -1.0f;                    // G:182-186
+  const float n_thc = mul * ((T_l / n_l) - (T_s / n_s));      // G:216
+  if (SPLIT) {
+    (a.pipe ? a.thc_scr : a.thc)[c] = n_thc;                  // G:262; thresholds follow in the scan / k_final
+  } else if (VARIANT == SBD_VARIANT_PYTHON) {
+    const int so = own_index<VARIANT>(a.g, gx, gy);
+    const float uu = __ldg(a.u + (size_t)s_lev * n2 + c), vv = __ldg(a.v + (size_t)s_lev * n2 + c);
+    float n_ws, n_wd;
+    wind_from_uv(a, uu, vv, n_ws, n_wd);
+    trigger_point<VARIANT>(a, c, n2, n_thc, n_ws, n_wd, a.theta[so] - a.gzsm[so]);
+  } else {
+    const float tp = a.prm.target_plev;
+    int lev = 0;
+    if (a.prm.level_scan == 0) {
+      float best = 0.0f;
+      for (int k = 0; k < a.nz; ++k) {
+        const float d = fabsf(__ldg(a.p + (size_t)k * n2 + c) - tp);
+        if (k == 0 || d < best) { best = d; lev = k; }
+      }
+    } else {
+      float diff = 1000000.0f;
+      for (int k = 0; k < a.nz; ++k) {
+        const float d = fabsf(__ldg(a.p + (size_t)k * n2 + c) - tp);
+        if (d <= diff) { lev = k; diff = d; } else break;
+      }
+    }
+    const float uu = __ldg(a.u + (size_t)lev * n2 + c), vv = __ldg(a.v + (size_t)lev * n2 + c);
+    float n_ws, n_wd;
+    wind_from_uv(a, uu, vv, n_ws, n_wd);
+    a.thc[c] = n_thc;
+    trigger_point<VARIANT>(a, c, n2, n_thc, n_ws, n_wd, 0.0f);
+  }
+}
+
+template <int VARIANT, bool SPLIT>
+__global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
+{
+  constexpr int TX = 64, TY = 32, NT = 512, CW = 4, NSX = TX / CW;
+  constexpr int NB = 64;      // strip buckets, index = largest radius in the strip (<= 56)
+  constexpr int SMALL = 6;    // strips below this radius hand their cells to the one-cell path
+  constexpr int NCB = 8;      // cell buckets: 0 = wider than the tile halo (global path), 1..5 = fixed
+                              // radius, 6 = any radius inside the tile (lone / irregular cells)
+  static_assert(TX * TY / CW == NT, "one strip per thread");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int R = a.R;
+  const int W = TX + 2 * R, Hh = TY + 2 * R;
+  const int WP = W + ((17 - (W & 15)) & 15);  // pairs per tile row, == 1 (mod 16): see phase 3
+  unsigned long long* s_t = reinterpret_cast<unsigned long long*>(smem_raw);
+  uint8_t* s_nn = reinterpret_cast<uint8_t*>(s_t + (size_t)WP * Hh);   // per tile cell: land<<7 | wide<<6 | nn
+  uint32_t* s_strip = reinterpret_cast<uint32_t*>(s_nn + TX * TY);     // nn_w << 16 | strip id
+  uint32_t* s_cell = s_strip + NT;                                      // byte << 16 | local cell id
+  __shared__ int s_cnt[NB], s_off[NB], s_ccnt[NCB], s_coff[NCB];
+  __shared__ int s_lev, s_nstrip, s_ncell;
+
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (SPLIT && a.order == 1 && !a.pipe) asm volatile("griddepcontrol.launch_dependents;");
+
+  if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {  // multi-GPU post / wait, as in k_trigger
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+      __threadfence_system();
+      if (a.sync_up) st_release_sys(a.sync_up + 1, a.sync_seq);
+      if (a.sync_dn) st_release_sys(a.sync_dn + 0, a.sync_seq);
+    }
+    const bool need_up = a.theta_up && (y0 - a.g.h < 0);
+    const bool need_dn = a.theta_dn && (y0 + TY + a.g.h > a.g.ny);
+    if (need_up || need_dn) {
+      if (tid == 0) {
+        if (need_up) wait_peer_flag(a.sync_local, 0, a.sync_seq);
+        if (need_dn) wait_peer_flag(a.sync_local, 1, a.sync_seq);
+      }
+      __syncthreads();
+    }
+  }
+
+  if (tid < NB) s_cnt[tid] = 0;
+  if (tid < NCB) s_ccnt[tid] = 0;
+  if (VARIANT == SBD_VARIANT_PYTHON && tid == NT - 1) {  // one level for the whole grid (P:228)
+    int lev = 0;
+    float best = fabsf(a.p[0] - a.prm.target_plev);
+    for (int k = 1; k < a.nz; ++k) {
+      const float d = fabsf(a.p[k] - a.prm.target_plev);
+      if (d < best) { best = d; lev = k; }
+    }
+    s_lev = lev;
+  }
+
+  // ---- phase 1: stage (t_land, t_sea) of the tile + halo, one warp per row ----
+  for (int ly = warp; ly < Hh; ly += NT / 32) {
+    const int gy = y0 - R + ly;
+    const float* trow = nullptr; const float* grow = nullptr; const uint16_t* crow = nullptr;
+    if (VARIANT == SBD_VARIANT_GENERIC) {
+      int gyl = gy;
+      if ((a.g.vh & 2) && gyl < 0) gyl = 0;
+      if ((a.g.vh & 4) && gyl >= a.g.ny) gyl = a.g.ny - 1;
+      const size_t rowoff = (size_t)min(max(gyl + a.g.h, 0), a.g.ldy - 1) * a.g.ldx;
+      trow = a.theta + rowoff;
+      if (gy < 0 && a.theta_up) trow = a.theta_up + (size_t)(a.ny_up + gy + a.g.h) * a.g.ldx;
+      else if (gy >= a.g.ny && a.theta_dn) trow = a.theta_dn + (size_t)(gy - a.g.ny + a.g.h) * a.g.ldx;
+      grow = a.gzsm + rowoff;
+      crow = a.code + rowoff;
+    }
+    unsigned long long* srow = s_t + (size_t)ly * WP;
+#pragma unroll 3
+    for (int lx = lane; lx < W; lx += 32) {
+      float th, gz; uint32_t cd;
+      if (VARIANT == SBD_VARIANT_GENERIC) {
+        int gx = x0 - R + lx;
+        if (a.g.vh & 1) gx = (gx < 0) ? gx + a.g.nx : ((gx >= a.g.nx) ? gx - a.g.nx : gx);
+        const int x = min(max(gx + a.g.h, 0), a.g.ldx - 1);
+        th = trow[x]; gz = grow[x]; cd = crow[x];
+      } else {
+        const int sidx = nbr_index<VARIANT>(a.g, x0 - R + lx, gy);
+        th = a.theta[sidx]; gz = a.gzsm[sidx]; cd = a.code[sidx];
+      }
+      const float t0 = th - gz;                                  // G:167
+      srow[lx] = (cd >> 15) ? pack2(t0, 0.0f) : pack2(0.0f, t0);
+    }
+  }
+
+  // ---- phase 2a: own cells, row-major (coalesced): radius byte; cells outside the zone are done ----
+  const size_t n2 = (size_t)a.g.nx * a.g.ny;
+#pragma unroll
+  for (int q = 0; q < TX * TY / NT; ++q) {
+    const int lid = q * NT + tid;
+    const int lx = lid % TX, ly = lid / TX;
+    const int gx = x0 + lx, gy = y0 + ly;
+    uint8_t b = 0;
+    if (gx < a.g.nx && gy < a.g.ny) {
+      const int so = own_index<VARIANT>(a.g, gx, gy);
+      const uint32_t cd = a.code[so];
+      const int nn = (int)(cd & 0x7fffu);
+      const size_t c = (size_t)gy * a.g.nx + gx;
+      if (nn == 0) {  // outside the coastal zone (G:174-176) or not processed (P:165)
+        if (VARIANT == SBD_VARIANT_GENERIC) {
+          a.sb[c] = a.prm.missing;
+        } else {
+          a.out[c] = a.prm.missing;                   // P:173
+          a.out[n2 + c] = a.theta[so] - a.gzsm[so];   // P:278
+          a.out[2 * n2 + c] = a.ws_in[c];             // P:279
+          a.out[3 * n2 + c] = a.wd_in[c];             // P:280
+        }
+        if (a.flags) a.flags[c] = 0;
+      } else {
+        b = (uint8_t)(((cd >> 15) << 7) | ((nn > R || nn > 62) ? 0x40u : (uint32_t)nn));
+      }
+    }
+    s_nn[lid] = b;
+  }
+  __syncthreads();
+
+  // ---- phase 2b: one strip per thread, column-major (vertical neighbours in adjacent lanes) ----
+  const int sx = tid / TY, sy = tid % TY;
+  const uint32_t nb4 = *reinterpret_cast<const uint32_t*>(s_nn + sy * TX + sx * CW);
+  int nnq[CW];
+  int nn_w = 0, nn_lo = 1 << 20, n_coast = 0;
+  bool any_wide = false;
+#pragma unroll
+  for (int q = 0; q < CW; ++q) {
+    const uint32_t b = (nb4 >> (8 * q)) & 0xffu;
+    nnq[q] = (b & 0x40u) ? -1 : (int)(b & 0x3fu);   // 0: not coastal, -1: wider than the halo
+    if (b & 0x40u) any_wide = true;
+    if (nnq[q] > 0) { nn_w = max(nn_w, nnq[q]); nn_lo = min(nn_lo, nnq[q]); ++n_coast; }
+  }
+  const bool as_strip = nn_w >= SMALL && n_coast >= 2 && nn_w - nn_lo <= 3;
+  int my_slot = -1;
+  int cslot[CW];
+  if (as_strip) my_slot = atomicAdd(&s_cnt[nn_w], 1);
+#pragma unroll
+  for (int q = 0; q < CW; ++q) {
+    cslot[q] = -1;
+    const int cb = (nnq[q] < 0) ? 0 : ((nnq[q] == 0 || as_strip) ? -1 : (nnq[q] < SMALL ? nnq[q] : 6));
+    if (cb >= 0) cslot[q] = atomicAdd(&s_ccnt[cb], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = NB - 1; k >= 0; --k) { s_off[k] = run; run += s_cnt[k]; }   // longest walks first
+    s_nstrip = run;
+    run = 0;
+    s_coff[0] = run; run += s_ccnt[0];
+    s_coff[6] = run; run += s_ccnt[6];
+    for (int k = SMALL - 1; k >= 1; --k) { s_coff[k] = run; run += s_ccnt[k]; }
+    s_coff[7] = run;
+    s_ncell = run;
+  }
+  __syncthreads();
+  if (as_strip) s_strip[s_off[nn_w] + my_slot] = ((uint32_t)nn_w << 16) | (uint32_t)tid;
+#pragma unroll
+  for (int q = 0; q < CW; ++q)
+    if (cslot[q] >= 0) {
+      const int cb = (nnq[q] < 0) ? 0 : (nnq[q] < SMALL ? nnq[q] : 6);
+      s_cell[s_coff[cb] + cslot[q]] = (((nb4 >> (8 * q)) & 0xffu) << 16) | (uint32_t)(sy * TX + sx * CW + q);
+    }
+  __syncthreads();
+
+  // ---- phase 3a: strips ----
+  if (tid < s_nstrip) {
+    const uint32_t ent = s_strip[tid];
+    const int sid = (int)(ent & 0xffffu), nw = (int)(ent >> 16);
+    const int ssx = sid / TY, ssy = sid % TY;
+    const uint32_t b4 = *reinterpret_cast<const uint32_t*>(s_nn + ssy * TX + ssx * CW);
+    int nq[CW];
+    uint32_t E[CW];  // per cell: which of the 6 + 6 edge columns of the walked row are in its window
+#pragma unroll
+    for (int q = 0; q < CW; ++q) {
+      const uint32_t b = (b4 >> (8 * q)) & 0xffu;
+      nq[q] = (b & 0x40u) ? 0 : (int)(b & 0x3fu);   // 0: nothing to sum for this cell
+      E[q] = 0u;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const int j = (i < 6) ? (-nw + i) : (nw - 8 + i);   // column offset from the strip's first cell
+        const int d = j - q;
+        if (nq[q] > 0 && d >= -nq[q] && d <= nq[q]) E[q] |= 1u << i;
+      }
+    }
+    unsigned long long acc[CW] = {0ull, 0ull, 0ull, 0ull};
+    const int lcy = R + ssy, lcx = R + ssx * CW;
+    const int kend = 2 * nw - 2;   // interior columns: walked-row index 6 .. 2 nw - 3
+    // rows |dy| <= nlo lie inside the windows of all coastal cells of the strip: no row predicate at
+    // all there (a cell that is not coastal accumulates values nobody reads)
+    int nlo = nw;
+#pragma unroll
+    for (int q = 0; q < CW; ++q) if (nq[q] > 0) nlo = min(nlo, nq[q]);
+    for (int dy = -nw; dy <= nw; ++dy) {
+      const unsigned long long* rp = s_t + (size_t)(lcy + dy) * WP + (lcx - nw);
+      const int ady = abs(dy);
+      if (ady <= nlo) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const unsigned long long v = rp[i];
+#pragma unroll
+          for (int q = 0; q < CW; ++q) add2_if(acc[q], v, E[q] & (1u << i));
+        }
+#pragma unroll 4
+        for (int k = 6; k < kend; ++k) {
+          const unsigned long long v = rp[k];
+#pragma unroll
+          for (int q = 0; q < CW; ++q) acc[q] = add2(acc[q], v);
+        }
+#pragma unroll
+        for (int i = 6; i < 12; ++i) {
+          const unsigned long long v = rp[kend - 6 + i];
+#pragma unroll
+          for (int q = 0; q < CW; ++q) add2_if(acc[q], v, E[q] & (1u << i));
+        }
+      } else {  // the (at most 3 + 3) outermost rows: switched per cell
+        uint32_t P[CW], m[CW];
+#pragma unroll
+        for (int q = 0; q < CW; ++q) { P[q] = (ady <= nq[q]) ? 1u : 0u; m[q] = P[q] ? E[q] : 0u; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const unsigned long long v = rp[i];
+#pragma unroll
+          for (int q = 0; q < CW; ++q) add2_if(acc[q], v, m[q] & (1u << i));
+        }
+#pragma unroll 2
+        for (int k = 6; k < kend; ++k) {
+          const unsigned long long v = rp[k];
+#pragma unroll
+          for (int q = 0; q < CW; ++q) add2_if(acc[q], v, P[q]);
+        }
+#pragma unroll
+        for (int i = 6; i < 12; ++i) {
+          const unsigned long long v = rp[kend - 6 + i];
+#pragma unroll
+          for (int q = 0; q < CW; ++q) add2_if(acc[q], v, m[q] & (1u << i));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CW; ++q)
+      if (nq[q] > 0) {
+        const int gx = x0 + ssx * CW + q, gy = y0 + ssy;
+        float T_l, T_s;
+        unpack2(acc[q], T_l, T_s);
+        const uint32_t c_l = a.cl[(size_t)gy * a.g.nx + gx];
+        const int wl = 2 * nq[q] + 1;
+        finish_cell<VARIANT, SPLIT>(a, gx, gy, ((b4 >> (8 * q + 7)) & 1u) != 0, T_l, T_s, c_l,
+                                    (uint32_t)(wl * wl) - c_l, s_lev);
+      }
+  }
+
+  // ---- phase 3b: single cells ----
+  const int n_cell = s_ncell;
+  for (int e = tid; e < n_cell; e += NT) {
+    const uint32_t ent = s_cell[e];
+    const int lid = (int)(ent & 0xffffu);
+    const uint32_t b = ent >> 16;
+    const int ly = lid / TX, lx = lid - ly * TX;
+    const int gx = x0 + lx, gy = y0 + ly;
+    const int lcx = R + lx, lcy = R + ly;
+    float T_l = 0.0f, T_s = 0.0f;
+    uint32_t c_l = 0, c_s = 0;
+    if (b & 0x40u) {  // wider than the tile halo: global path
+      const int nn = (int)(a.code[own_index<VARIANT>(a.g, gx, gy)] & 0x7fffu);
+      window_sums_global<VARIANT>(a, gx, gy, nn, T_l, T_s, c_l, c_s);
+    } else {
+      const int nn = (int)(b & 0x3fu);
+      unsigned long long acc = 0ull;
+      switch (nn) {
+        case 1: acc = window_fixed2<1>(s_t, WP, lcx, lcy); break;
+        case 2: acc = window_fixed2<2>(s_t, WP, lcx, lcy); break;
+        case 3: acc = window_fixed2<3>(s_t, WP, lcx, lcy); break;
+        case 4: acc = window_fixed2<4>(s_t, WP, lcx, lcy); break;
+        case 5: acc = window_fixed2<5>(s_t, WP, lcx, lcy); break;
+        default: {
+          const int wl = 2 * nn + 1;
+          for (int r = 0; r < wl; ++r) {
+            const unsigned long long* rp = s_t + (size_t)(lcy - nn + r) * WP + lcx - nn;
+#pragma unroll 4
+            for (int j = 0; j < wl; ++j) acc = add2(acc, rp[j]);
+          }
+        }
+      }
+      unpack2(acc, T_l, T_s);
+      c_l = a.cl[(size_t)gy * a.g.nx + gx];
+      const int wl = 2 * nn + 1;
+      c_s = (uint32_t)(wl * wl) - c_l;
+    }
+    finish_cell<VARIANT, SPLIT>(a, gx, gy, (b & 0x80u) != 0, T_l, T_s, c_l, c_s, s_lev);
+  }
+
+  if (SPLIT && a.pipe) {  // pipelined steps: see the end of k_trigger
+    if (tid == 0) {
+      const unsigned n_cta = gridDim.x * gridDim.y;
+      if (atomicAdd(a.pipe_ctr, 1u) == n_cta - 1u) {
+        *a.pipe_ctr = 0u;
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;");
       }
@@ -2019,6 +2441,8 @@ struct sbd_plan {
   // static planes
   float* d_gzsm = nullptr;
   uint16_t* d_code = nullptr;
+  uint32_t* d_cl = nullptr;   // land cells in every coastal-zone cell's final window (k_static_counts)
+  int window_kernel = 0;      // sbd_plan_set_window_kernel: 0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4)
   float* d_stats = nullptr;   // 4 floats
   float* d_carry = nullptr;   // 5 floats
   int* d_cnt = nullptr;       // nn_max, n_coastal, n_active (compaction)
@@ -2369,9 +2793,56 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
 // that precedes it in the stream.  Two tile shapes: 64x16 cells with a halo of up to 16 (coarse
 // grids: N512, 0.1 degree, ERA-Interim) and 128x64 cells with a halo of up to 56 (km-scale grids,
 // where the search radius reaches k+1 = 55 cells).
+int g_window_kernel_default = 0;  // sbd_set_window_kernel_default
+
+// strip form of the window kernel (k_win4): tile 64 x 32, 512 threads
+template <int VARIANT>
+int launch_win4(sbd_plan* p, TrigArgs& a)
+{
+  constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
+  constexpr int TX = 64, TY = 32, NT = 512;
+  const int R = a.R;
+  const int W = TX + 2 * R, Hh = TY + 2 * R;
+  const int WP = W + ((17 - (W & 15)) & 15);
+  const size_t smem = (size_t)WP * Hh * 8 + TX * TY + (size_t)(NT + TX * TY) * 4;
+  auto kern = k_win4<VARIANT, GEN>;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+  a.nws = p->d_nws;
+  a.nwd = p->d_nwd;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = p->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = (GEN && (a.order == 0 || a.pipe) && !p->timing) ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+  CK(cudaLaunchKernelEx(&cfg, kern, (const TrigArgs)a)); LAUNCHED();
+  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+  if (GEN && a.order == 0) {
+    if (p->timing) CK(cudaEventRecord(p->ev[4], p->stream));
+    if (p->n_coastal > 0) {
+      k_final<<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
+    }
+    if (p->timing) CK(cudaEventRecord(p->ev[5], p->stream));
+  }
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+
 template <int VARIANT>
 int launch_trigger(sbd_plan* p, TrigArgs& a)
 {
+  // radii beyond a few cells: strip kernel (see k_win4); sbd_plan_set_window_kernel overrides
+  static int win4_min = -1;
+  if (win4_min < 0) { const char* e = getenv("SBD_WIN4_MIN"); win4_min = e ? atoi(e) : 9; }
+  const int mode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
+  const bool strips = mode == 2 || (mode == 0 && a.R >= win4_min);
+  if (strips && a.R <= 56) return launch_win4<VARIANT>(p, a);
   if (a.R <= 16) {
     static int tile = -1;
     if (tile < 0) { const char* e = getenv("SBD_TILE"); tile = e ? atoi(e) : 0; }
@@ -2499,6 +2970,7 @@ int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, 
   const size_t n = plane_elems(p);
   if (cudaMalloc((void**)&p->d_gzsm, n * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_code, n * sizeof(uint16_t)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_cl, (size_t)nx * ny * sizeof(uint32_t)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_stats, 4 * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_carry, 5 * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_cnt, 4 * sizeof(int)) != cudaSuccess ||
@@ -2518,7 +2990,7 @@ void sbd_plan_destroy(sbd_plan* p)
 {
   if (!p) return;
   if (p->own_stream) cudaStreamSynchronize(p->own_stream);
-  cudaFree(p->d_gzsm); cudaFree(p->d_code); cudaFree(p->d_stats); cudaFree(p->d_carry); cudaFree(p->d_cnt);
+  cudaFree(p->d_gzsm); cudaFree(p->d_code); cudaFree(p->d_cl); cudaFree(p->d_stats); cudaFree(p->d_carry); cudaFree(p->d_cnt);
   cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads); cudaFree(p->d_nws); cudaFree(p->d_nwd);
   for (int i = 0; i < 6; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
@@ -2557,6 +3029,19 @@ int sbd_plan_set_peer_sync(sbd_plan* p, uint32_t* sync_local, uint32_t* sync_up,
   if (!sync_local && (sync_up || sync_dn)) return fail(SBD_EINVAL, "neighbour flags without local flags");
   p->sync_local = sync_local; p->sync_up = sync_up; p->sync_dn = sync_dn;
   p->sync_seq = 0;
+  return SBD_OK;
+}
+int sbd_set_window_kernel_default(int mode)
+{
+  if (mode < 0 || mode > 2) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 strips");
+  g_window_kernel_default = mode;
+  return SBD_OK;
+}
+int sbd_plan_set_window_kernel(sbd_plan* p, int mode)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  if (mode < 0 || mode > 2) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 strips");
+  p->window_kernel = mode;
   return SBD_OK;
 }
 int sbd_plan_set_pipelined(sbd_plan* p, int on)
@@ -2641,6 +3126,12 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
                                                            max(p->nx, p->ny), p->ny - 1, p->d_cnt, p->d_cnt + 1);
   }
   LAUNCHED();
+  {
+    dim3 gc(cdiv(p->nx, 128), p->ny);
+    if (p->variant == SBD_VARIANT_GENERIC) k_static_counts<SBD_VARIANT_GENERIC><<<gc, 128, 0, st>>>(p->d_code, p->d_cl, p->g);
+    else k_static_counts<SBD_VARIANT_PYTHON><<<gc, 128, 0, st>>>(p->d_code, p->d_cl, p->g);
+    LAUNCHED();
+  }
   CK(cudaGetLastError());
   if (p->variant == SBD_VARIANT_GENERIC) {
     // compacted list of coastal-zone cells, raster order (static)
@@ -2761,7 +3252,7 @@ int sbd_plan_step_scan(sbd_plan* p, const float* pp, const float* u, const float
   if ((rc = in_view(p, u, n3, &a.u, true))) return rc;
   if ((rc = in_view(p, v, n3, &a.v, true))) return rc;
   a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny;
-  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code; a.cl = p->d_cl;
   p->cur_p = a.p; p->cur_u = a.u; p->cur_v = a.v;
   a.order = 0; p->last_order = 0;
   if ((rc = launch_scan(p, a))) return rc;
@@ -2791,7 +3282,7 @@ int sbd_plan_step_finish(sbd_plan* p, float timestep, int step, const float* the
   a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny;
   a.first_step = step < 2 ? 1 : 0;
   a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
-  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code; a.cl = p->d_cl;
   a.theta_up = p->peer_up; a.theta_dn = p->peer_dn; a.ny_up = p->peer_ny_up;
   if (p->sync_local && (p->peer_up || p->peer_dn)) {  // one post / wait per step, inside the window kernel
     a.sync_local = p->sync_local; a.sync_up = p->peer_up ? p->sync_up : nullptr;
@@ -2837,7 +3328,7 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
   a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny;
   a.first_step = step < 2 ? 1 : 0;
   a.six_hourly = six_hourly_flag(step, timestep, p->prm.target_time);
-  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code; a.cl = p->d_cl;
   a.theta_up = p->peer_up; a.theta_dn = p->peer_dn; a.ny_up = p->peer_ny_up;
   if (p->sync_local && (p->peer_up || p->peer_dn)) {  // one post / wait per step, inside the window kernel
     a.sync_local = p->sync_local; a.sync_up = p->peer_up ? p->sync_up : nullptr;
@@ -2941,7 +3432,7 @@ int sbd_plan_step_py(sbd_plan* p, int step, float timestep_min, const float* pp,
   a.g = p->g; a.nz = p->nz; a.R = p->R; a.rows_processed = p->ny - 1;
   a.first_step = step < 2 ? 1 : 0;
   a.six_hourly = six_hourly_flag(step, timestep_min * 60.0f, p->prm.target_time);  // P:146, P:271
-  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code;
+  a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code; a.cl = p->d_cl;
   if ((rc = launch_trigger<SBD_VARIANT_PYTHON>(p, a))) return rc;
   return flush_out(p, pend, any_host);
 }

@@ -154,6 +154,10 @@ class Plan:
         previous step call is issued).  See sbd_plan_set_pipelined."""
         _capi.check(self.lib.sbd_plan_set_pipelined(self._h, 1 if on else 0), "plan_set_pipelined")
 
+    def set_window_kernel(self, mode):
+        """0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4).  See sbd_plan_set_window_kernel."""
+        _capi.check(self.lib.sbd_plan_set_window_kernel(self._h, int(mode)), "plan_set_window_kernel")
+
     def use_own_stream(self):
         _capi.check(self.lib.sbd_plan_use_own_stream(self._h), "plan_use_own_stream")
 

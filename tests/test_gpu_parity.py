@@ -6,7 +6,7 @@ import pytest
 
 from seabreeze_param_b200 import generic, seabreeze, seabreezediag, synth
 from seabreeze_param_b200._capi import SBD_VARIANT_GENERIC, SBD_VARIANT_PYTHON, load
-from util import assert_bits_equal, generic_case, generic_step_inputs
+from util import window_kernel, assert_bits_equal, generic_case, generic_step_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -98,8 +98,14 @@ def test_exact_parallel_stats_adversarial(oracle):
         assert_bits_equal(sm_o, sm_g, "sigmoid: " + nm)
 
 
-@pytest.mark.parametrize("name", ["t_py", "c5"])
-def test_py_diag_time_loop(oracle, name):
+@pytest.mark.parametrize("name,wk", [("t_py", 0), ("c5", 0), ("t_py", 2), ("c5", 2)])
+def test_py_diag_time_loop(oracle, name, wk):
+    """wk = 2 forces the strip window kernel (k_win4) on these small-radius grids."""
+    with window_kernel(wk):
+        _py_diag_time_loop(oracle, name)
+
+
+def _py_diag_time_loop(oracle, name):
     cfg = synth.CONFIGS[name]
     land, ice, lon, lat, z, sig = synth.static_fields(cfg)
     coast = oracle.py_get_edges(land, ice)
@@ -122,6 +128,32 @@ def test_py_diag_time_loop(oracle, name):
         ws_g, wd_g = np.ascontiguousarray(gc[2]), np.ascontiguousarray(gc[3])
         trig += int((f & 2).sum())
     assert trig > 0
+
+
+@pytest.mark.parametrize("wk", [0, 1])
+def test_py_diag_mid_radius(oracle, wk):
+    """Python variant on a 0.5-degree grid: get_dist radius k = 9, search radii up to ~10 cells, so
+    the automatic choice (wk = 0) is the strip window kernel with real 4-cell strips; wk = 1 is the
+    tile kernel.  Same bits as the oracle's literal growing-window loops either way."""
+    cfg = synth.Config("t_py_mid", 720, 361, 9, 0, "python", 10.0, False, 60.0, "0.5 degree python-variant test")
+    land, ice, lon, lat, z, sig = synth.static_fields(cfg)
+    coast = oracle.py_get_edges(land, ice)
+    cd = oracle.py_get_dist(coast, land, lon, lat, literal=False)
+    ws_o = np.zeros_like(z); wd_o = np.zeros_like(z)
+    ws_g = np.zeros_like(z); wd_g = np.zeros_like(z)
+    with window_kernel(wk):
+        for step in (1, 2, 6):
+            theta, p, u, v = synth.step_fields(cfg, step, land, z, lat)
+            o, f = oracle.py_diag(step, p, z, sig, theta, v, u, cd, ws_o, wd_o, timestep=cfg.timestep, literal=True)
+            fl = np.zeros((cfg.nx, cfg.ny), np.uint8, order="F")
+            g = seabreeze.diag(step, p, F(z), F(sig), F(theta), F(v), F(u), F(cd), F(ws_g), F(wd_g),
+                               F(np.zeros_like(z)), timestep=cfg.timestep, flags=fl)
+            gc = seabreezediag.c2f(g)
+            for k, nm in enumerate(("sb_con", "t0", "windspeed", "winddir")):
+                assert_bits_equal(o[k], gc[k], "%s step %d" % (nm, step))
+            assert np.array_equal(f, seabreezediag.c2f(fl)), "flags step %d" % step
+            ws_o, wd_o = o[2].copy(), o[3].copy()
+            ws_g, wd_g = np.ascontiguousarray(gc[2]), np.ascontiguousarray(gc[3])
 
 
 def test_py_wrapper_diag_matches_manual_loop(oracle):
@@ -203,8 +235,15 @@ def test_generic_edges_dist(oracle, name):
     assert_bits_equal(mo, mg, "get_edges swap=False")
 
 
-@pytest.mark.parametrize("name,level_scan", [("t_gen", 0), ("t_gen", 1), ("c1", 0)])
-def test_generic_seabreeze_diag_steps(oracle, name, level_scan):
+@pytest.mark.parametrize("name,level_scan,wk", [("t_gen", 0, 0), ("t_gen", 1, 0), ("c1", 0, 0), ("t_gen", 0, 2),
+                                                 ("t_gen", 1, 2), ("c1", 0, 2)])
+def test_generic_seabreeze_diag_steps(oracle, name, level_scan, wk):
+    """wk = 2 forces the strip window kernel (k_win4) on these small-radius grids."""
+    with window_kernel(wk):
+        _generic_seabreeze_diag_steps(oracle, name, level_scan)
+
+
+def _generic_seabreeze_diag_steps(oracle, name, level_scan):
     cfg = synth.CONFIGS[name]
     case = generic_case(cfg, oracle)
     ny, nx = cfg.ny, cfg.nx
@@ -406,14 +445,17 @@ def test_generic_device_pointers_torch(oracle):
     plan.close()
 
 
+@pytest.mark.parametrize("wk", [0, 1])
 @pytest.mark.parametrize("nx,ny,h,filt,expect", [(160, 96, 24, 14.0, "big tile"), (320, 240, 54, 40.0, "big tile"),
                                                    (300, 200, 72, 60.0, "global path")])
-def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect):
-    """km-scale regional grids (config 3): the final search radius reaches tens of cells.  Radii up to
-    16 use the 64x16 tile, up to 56 the 128x64 tile, beyond that the global-memory path."""
+def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
+    """km-scale regional grids (config 3): the final search radius reaches tens of cells.  wk = 0: the
+    strip kernel (k_win4, radii up to 56 in shared memory, beyond that the global-memory path);
+    wk = 1: the tile kernel (k_trigger, 128x64 tile with patch-raster order)."""
     cfg = synth.Config("t_big", nx, ny, 4, h, "generic", filt, True, 1440.0, "wide-window test")
     case = generic_case(cfg, oracle)
     plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
+    plan.set_window_kernel(wk)
     plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
     nn_max = plan.info()["nn_max"]
     assert nn_max > 16, plan.info()

@@ -41,3 +41,19 @@ def generic_step_inputs(cfg, case, step, oracle, seed=0):
     theta_h = synth.pad_halo(theta, cfg.h)
     oracle.swap_bounds(theta_h, cfg.h)
     return theta_h, p, u, v
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def window_kernel(mode):
+    """Process-wide form of the window-sum kernel for the duration of a test: 0 automatic, 1 tile
+    kernel (k_trigger), 2 strip kernel (k_win4).  Both must give the oracle's bits."""
+    from seabreeze_param_b200 import _capi
+    lib = _capi.load()
+    _capi.check(lib.sbd_set_window_kernel_default(int(mode)), "set_window_kernel_default")
+    try:
+        yield
+    finally:
+        lib.sbd_set_window_kernel_default(0)

@@ -1,5 +1,4 @@
-python -m pytest tests -m gpu -x -q -k "wide or mid_radius or time_loop or seabreeze_diag_steps or golden" 2>&1 | tail -3 > gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -x -q --durations=8 2>&1 | tail -16 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
-timeout 300 python scripts/probe_py.py c4 3 > gpurun_out/probe_c4.log 2>&1; grep -E "us/step|checksum" gpurun_out/probe_c4.log
-timeout 300 python scripts/probe_step.py c3 2>&1 | grep -E "wall|per-kernel" | cut -c1-160 > gpurun_out/probe_c3_strip.log
-cat gpurun_out/probe_c3_strip.log
+SBD_WIN4_MIN=1 timeout 200 python scripts/probe_step.py c2 2>&1 | grep -E "wall|per-kernel" | cut -c1-160 > gpurun_out/probe_c2_win4.log
+cat gpurun_out/probe_c2_win4.log

@@ -1,0 +1,159 @@
+"""Parity at BASELINE.json's full grid sizes.
+
+c2 (1024x769x70, generic) and c4 (3600x1800, python variant, radii up to 22 cells) are compared with the
+oracle's literal loops bit for bit.  c3 (4000x3000, radii up to 54) is too large for the oracle's
+growing-window loops, so it is covered by size-independent properties: the two independent window
+kernels (tile form k_trigger, strip form k_win4) must agree bit for bit, a repeated step must
+reproduce itself, and a row block cut out of the result must equal the oracle run on that block
+with halos taken from the full fields."""
+import numpy as np
+import pytest
+
+from seabreeze_param_b200 import generic, seabreeze, seabreezediag, synth
+from seabreeze_param_b200._capi import SBD_VARIANT_GENERIC
+from util import assert_bits_equal, generic_case, generic_step_inputs
+
+pytestmark = pytest.mark.gpu
+F = lambda a: np.asfortranarray(a.T) if a.ndim == 2 else np.asfortranarray(a.transpose(2, 1, 0))
+
+
+def test_c2_full_size_vs_oracle(oracle):
+    """BASELINE configs[1], the benchmark workload: three steps (first, ordinary, 6-hourly)."""
+    cfg = synth.CONFIGS["c2"]
+    oracle.set_threads(oracle.max_threads())
+    try:
+        case = generic_case(cfg, oracle)
+        ny, nx = cfg.ny, cfg.nx
+        plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
+        plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
+        so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+        sp = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+        trig = 0
+        for step in (1, 2, 15):
+            theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
+            fo = oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"],
+                                       case["sigma_h"], *so, cfg.h, literal=True)
+            fp = np.zeros((ny, nx), np.uint8)
+            plan.step(cfg.timestep, step, p, u, v, theta_h, *sp, flags=fp)
+            for a, b, nm in zip(so, sp, ("windspeed", "winddir", "thc", "sb_con")):
+                assert_bits_equal(a, b, "c2 %s step %d" % (nm, step))
+            assert np.array_equal(fo, fp), "c2 flags step %d" % step
+            trig += int((fo & 2).sum())
+        assert trig > 0
+        plan.close()
+    finally:
+        oracle.set_threads(1)
+
+
+def test_c4_full_size_vs_oracle(oracle):
+    """BASELINE configs[3] grid (0.1 degree, 3600x1800, python variant): get_edges, get_dist and two
+    records of diag (the second one a 6-hourly step) against the oracle's literal loops."""
+    cfg = synth.CONFIGS["c4"]
+    oracle.set_threads(oracle.max_threads())
+    try:
+        land, ice, lon, lat, z, sig = synth.static_fields(cfg)
+        coast_o = oracle.py_get_edges(land, ice)
+        cd_o = oracle.py_get_dist(coast_o, land, lon, lat, literal=False)
+        coast_g = seabreeze.get_edges(F(land), F(ice))
+        assert_bits_equal(coast_o, seabreezediag.c2f(coast_g), "c4 coast")
+        cd_g = seabreeze.get_dist(coast_g, F(land), lon, lat)
+        assert_bits_equal(cd_o, seabreezediag.c2f(cd_g), "c4 cdist")
+        ws_o = np.zeros_like(z); wd_o = np.zeros_like(z)
+        ws_g = np.zeros_like(z); wd_g = np.zeros_like(z)
+        theta, p, u, v = synth.step_fields(cfg, 1, land, z, lat)
+        for step in (1, 6):
+            if step == 6:  # a second record without regenerating 37 levels: perturb deterministically
+                theta = (theta + np.float32(0.75) * np.roll(land, 3, axis=1)).astype(np.float32)
+                u = np.ascontiguousarray(u[:, ::-1, :]); v = np.ascontiguousarray(v[:, :, ::-1])
+            o, f = oracle.py_diag(step, p, z, sig, theta, v, u, cd_o, ws_o, wd_o, timestep=cfg.timestep, literal=True)
+            fl = np.zeros((cfg.nx, cfg.ny), np.uint8, order="F")
+            g = seabreeze.diag(step, p, F(z), F(sig), F(theta), F(v), F(u), cd_g, F(ws_g), F(wd_g),
+                               F(np.zeros_like(z)), timestep=cfg.timestep, flags=fl)
+            gc = seabreezediag.c2f(g)
+            for k, nm in enumerate(("sb_con", "t0", "windspeed", "winddir")):
+                assert_bits_equal(o[k], gc[k], "c4 %s step %d" % (nm, step))
+            assert np.array_equal(f, seabreezediag.c2f(fl)), "c4 flags step %d" % step
+            ws_o, wd_o = o[2].copy(), o[3].copy()
+            ws_g, wd_g = np.ascontiguousarray(gc[2]), np.ascontiguousarray(gc[3])
+    finally:
+        oracle.set_threads(1)
+
+
+def test_c3_full_size_properties(oracle):
+    """BASELINE configs[2] grid (4000x3000, halo 54, radii up to 54 cells; two levels to keep the test
+    small).  (1) tile window kernel == strip window kernel, bit for bit; (2) the step reproduces
+    itself; (3) a 96-row block run as its own plan (halo rows cut from the full fields) gives the
+    full grid's rows, and equals the oracle on that block."""
+    import torch
+    cfg = synth.Config("c3_2lev", 4000, 3000, 2, 54, "generic", 40.0, True, 1440.0, "c3 grid, 2 levels")
+    h, nx, ny, nz = cfg.h, cfg.nx, cfg.ny, cfg.nz
+    dev = torch.device("cuda:0")
+    land, ice, lon, lat, z, sig = synth.static_fields(cfg)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    mask_h = torch.zeros((ny + 2 * h, nx + 2 * h), dtype=torch.float32, device=dev)
+    generic.get_edges(mask_h, t(ice), t(land), h)
+    cdist = torch.empty((ny, nx), dtype=torch.float32, device=dev)
+    generic.get_dist(mask_h, t(land), t(lon), t(lat), 180.0, cdist, h)
+
+    def haloed(a2d):
+        f = torch.zeros((ny + 2 * h, nx + 2 * h), dtype=torch.float32, device=dev)
+        f[h:h + ny, h:h + nx] = a2d
+        generic.swap_bounds(f, h)
+        return f
+
+    mk, zh, sh = haloed(cdist), haloed(t(z)), haloed(t(sig))
+    theta, p, u, v = synth.step_fields(cfg, 1, land, z, lat)
+    th, dp, du, dv = haloed(t(theta)), t(p), t(u), t(v)
+    res = {}
+    stats = None
+    for wk in (1, 2, 2):
+        plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, nz, h)
+        plan.set_window_kernel(wk)
+        plan.set_static(mk, zh, sh)
+        info = plan.info()
+        assert info["nn_max"] >= 50, info
+        stats = np.array([info["mean"], info["std2inv"], info["r"]], np.float32)
+        st = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(4)]
+        for step in (1, 2):
+            plan.step(cfg.timestep, step, dp, du, dv, th, *st)
+        plan.sync()
+        out = [s.cpu().numpy() for s in st]
+        if wk in res:
+            for a, b, nm in zip(res[wk], out, ("windspeed", "winddir", "thc", "sb_con")):
+                assert_bits_equal(a, b, "c3 repeat %s" % nm)      # (2) determinism
+        res[wk] = out
+        plan.close()
+    for a, b, nm in zip(res[1], res[2], ("windspeed", "winddir", "thc", "sb_con")):
+        assert_bits_equal(a, b, "c3 tile vs strip kernel %s" % nm)  # (1)
+    assert np.isfinite(res[2][3]).all() and (res[2][3] != 0).any()
+    # (3a) a 96-row block run as its own plan (halo rows cut from the full planes, the full grid's sigma
+    # statistics injected) reproduces the full-grid rows: the result is decomposition-independent
+    r0, nb = 1500, 96
+    cut = lambda f: np.ascontiguousarray(f[r0:r0 + nb + 2 * h].cpu().numpy())
+    pb, ub, vb = (np.ascontiguousarray(x[:, r0:r0 + nb]) for x in (p, u, v))
+    mk_b, zh_b, sh_b, th_b = cut(mk), cut(zh), cut(sh), cut(th)
+    plan = generic.Plan(SBD_VARIANT_GENERIC, nx, nb, nz, h)
+    plan.set_static(mk_b, zh_b, sh_b, stats=stats)
+    sb = [np.zeros((nb, nx), np.float32) for _ in range(4)]
+    for step in (1, 2):
+        plan.step(cfg.timestep, step, pb, ub, vb, th_b, *sb)
+    for a, b, nm in zip(res[2], sb, ("windspeed", "winddir", "thc", "sb_con")):
+        assert_bits_equal(a[r0:r0 + nb], b, "c3 row block vs full grid %s" % nm)
+    plan.close()
+    # (3b) the same block with its own statistics == the oracle (final-window evaluation) on the block
+    oracle.set_threads(oracle.max_threads())
+    try:
+        plan = generic.Plan(SBD_VARIANT_GENERIC, nx, nb, nz, h)
+        plan.set_static(mk_b, zh_b, sh_b)
+        so = [np.zeros((nb, nx), np.float32) for _ in range(4)]
+        sg = [np.zeros((nb, nx), np.float32) for _ in range(4)]
+        for step in (1, 2):
+            fo = oracle.seabreeze_diag(cfg.timestep, step, pb, ub, vb, th_b, mk_b, zh_b, sh_b, *so, h, literal=False)
+            fg = np.zeros((nb, nx), np.uint8)
+            plan.step(cfg.timestep, step, pb, ub, vb, th_b, *sg, flags=fg)
+            for a, b, nm in zip(so, sg, ("windspeed", "winddir", "thc", "sb_con")):
+                assert_bits_equal(a, b, "c3 block vs oracle %s step %d" % (nm, step))
+            assert np.array_equal(fo, fg)
+        plan.close()
+    finally:
+        oracle.set_threads(1)

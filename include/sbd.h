@@ -75,6 +75,11 @@ int sbd_device_count(void);
  * m1 (optional, nx*ny bytes): binarised land/ice mask (G:325-337). */
 int sbd_get_edges_f32(float* mask, const float* icefrac, const float* landfrac, int nx, int ny, int h,
                       int swap, uint8_t* m1);
+/* get_edges plus two optional by-products of its Sobel stencil: px, py
+ * (nx*ny each, may be NULL) receive the Sobel components of generic/sea_breeze_diag.f90:350-357;
+ * atan2(py, px) is the direction of the coastline normal.  Not outputs of the reference routine. */
+int sbd_get_edges_ex_f32(float* mask, const float* ice, const float* land, int nx, int ny, int h, int swap,
+                         uint8_t* m1, float* px, float* py);
 
 /* get_dist(coast, landfrac, lon, lat, maxdist, cdist, halo_size)  G:375-455.
  * coast: halo'd output of get_edges; landfrac, cdist: nx x ny; lon(nx), lat(ny) in degrees.
@@ -214,6 +219,12 @@ int sbd_plan_set_static(sbd_plan* plan, const float* mask, const float* z, const
                         const float* stats_in);
 /* Largest search radius found by set_static and the sigmoid statistics (mean, 2/sigma, r, var). */
 int sbd_plan_info(sbd_plan* plan, int* nn_max, int* n_coastal, float* stats4);
+
+/* By-products of the static planes (any pointer may be NULL; int32, nx*ny,
+ * host or device): nn = the search radius at which the growing-window loop of
+ * generic/sea_breeze_diag.f90:188-214 stops for each cell, n_land / n_sea = its counters n_l, n_s at
+ * that pass; all 0 outside the coastal zone. */
+int sbd_plan_window_info(sbd_plan* plan, int* nn, int* n_land, int* n_sea);
 
 /* Number of aligned 4-cell groups with at least one coastal-zone cell (the units the level scan
  * streams; 16 bytes per group and level).  -1 before sbd_plan_set_static. */

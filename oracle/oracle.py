@@ -39,6 +39,8 @@ def lib():
         L.orc_swap_bounds.argtypes = [fp, i, i, i]
         L.orc_get_edges.argtypes = [fp, fp, fp, i, i, i, i, vp]
         L.orc_get_dist.argtypes = [fp, fp, fp, fp, f, fp, i, i, i, i]
+        L.orc_sobel.argtypes = [fp, i, i, i, fp, fp]
+        L.orc_window_info.argtypes = [fp, i, i, i, f, vp, vp, vp]
         L.orc_seabreeze_diag.argtypes = [f, i] + [fp] * 11 + [i, i, i, i, i, i, vp]
         _lib = L
     return _lib
@@ -134,6 +136,28 @@ def get_edges(icefrac, landfrac, h, swap=True, mask_in=None):
     if rc:
         raise RuntimeError("orc_get_edges status %d" % rc)
     return mask, m1
+
+
+def sobel(mask_h, h):
+    """(px, py) of generic/sea_breeze_diag.f90:350-357 on a halo'd binary mask."""
+    m = _c(mask_h)
+    ny, nx = m.shape[0] - 2 * h, m.shape[1] - 2 * h
+    px = np.zeros((ny, nx), np.float32); py = np.zeros((ny, nx), np.float32)
+    rc = lib().orc_sobel(_p(m), nx, ny, h, _p(px), _p(py))
+    if rc:
+        raise RuntimeError("orc_sobel status %d" % rc)
+    return px, py
+
+
+def window_info(mask_h, h, maxdist=180.0):
+    """(nn, n_land, n_sea) at the last pass of the growing-window loop, G:188-214; int32 (ny, nx)."""
+    m = _c(mask_h)
+    ny, nx = m.shape[0] - 2 * h, m.shape[1] - 2 * h
+    out = [np.zeros((ny, nx), np.int32) for _ in range(3)]
+    rc = lib().orc_window_info(_p(m), nx, ny, h, float(maxdist), *[o.ctypes.data for o in out])
+    if rc:
+        raise RuntimeError("orc_window_info status %d" % rc)
+    return out
 
 
 def get_dist(coast_h, landfrac, lon, lat, maxdist, h, literal=True):

@@ -135,7 +135,8 @@ __global__ void k_binarise_generic(float* __restrict__ mask, const float* __rest
 // Sobel on the halo'd binary mask (G:348-366): coast = (px != 0 || py != 0).  Values are small
 // integers, exactly representable, so integer arithmetic is bit-equivalent to the fp32 original.
 __global__ void k_sobel_generic(const float* __restrict__ mask, float* __restrict__ coast, int nx,
-                                int ny, int h)
+                                int ny, int h, float* __restrict__ px_out = nullptr,
+                                float* __restrict__ py_out = nullptr)
 {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
@@ -148,6 +149,26 @@ __global__ void k_sobel_generic(const float* __restrict__ mask, float* __restric
   const float px = (r0[1] - r0[-1]) + 2.0f * (r1[1] - r1[-1]) + (r2[1] - r2[-1]);
   const float py = (r2[-1] - r0[-1]) + 2.0f * (r2[0] - r0[0]) + (r2[1] - r0[1]);
   coast[(size_t)y * nx + x] = (px != 0.0f || py != 0.0f) ? 1.0f : 0.0f;
+  // optional by-product: the Sobel components themselves, atan2(py, px) being the
+  // direction of the coastline normal.  Small integers: exact in any evaluation order.
+  if (px_out) px_out[(size_t)y * nx + x] = px;
+  if (py_out) py_out[(size_t)y * nx + x] = py;
+}
+
+// by-product of the static planes: final search radius and land / sea counts of the final window
+__global__ void k_window_info(const uint16_t* __restrict__ code, const uint32_t* __restrict__ cl, int nx, int ny,
+                              int h, int ldx, int* __restrict__ nn_out, int* __restrict__ nl_out,
+                              int* __restrict__ ns_out)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= nx) return;
+  const size_t c = (size_t)y * nx + x;
+  const int nn = (int)(code[(size_t)(y + h) * ldx + (x + h)] & 0x7fffu);
+  const int n_l = (int)cl[c];
+  const int wl = 2 * nn + 1;
+  if (nn_out) nn_out[c] = nn;
+  if (nl_out) nl_out[c] = nn ? n_l : 0;
+  if (ns_out) ns_out[c] = nn ? wl * wl - n_l : 0;
 }
 
 __global__ void k_copy_interior(float* __restrict__ dst_h, const float* __restrict__ src, int nx, int ny,
@@ -3225,6 +3246,24 @@ int sbd_plan_info(sbd_plan* p, int* nn_max, int* n_coastal, float* stats4)
   return SBD_OK;
 }
 
+int sbd_plan_window_info(sbd_plan* p, int* nn, int* n_land, int* n_sea)
+{
+  if (!p || !p->have_static) return fail(SBD_EINVAL, "plan has no static fields yet");
+  Tmp t;
+  t.st = p->stream;
+  const size_t n2 = (size_t)p->nx * p->ny;
+  void *d_nn, *d_nl, *d_ns;
+  int rc;
+  if ((rc = t.out(nn, n2 * 4, false, &d_nn))) return rc;
+  if ((rc = t.out(n_land, n2 * 4, false, &d_nl))) return rc;
+  if ((rc = t.out(n_sea, n2 * 4, false, &d_ns))) return rc;
+  dim3 g(cdiv(p->nx, 128), p->ny);
+  k_window_info<<<g, 128, 0, t.st>>>(p->d_code, p->d_cl, p->nx, p->ny, p->variant == SBD_VARIANT_GENERIC ? p->h : 0,
+                                     p->g.ldx, (int*)d_nn, (int*)d_nl, (int*)d_ns); LAUNCHED();
+  CK(cudaGetLastError());
+  return t.finish();
+}
+
 int sbd_plan_n_quads(sbd_plan* p) { return (p && p->have_static) ? p->n_quads : -1; }
 int sbd_plan_host_split(sbd_plan* p, int* ysplit, int* n_quads_north)
 {
@@ -3601,6 +3640,12 @@ int sbd_py_diag_loop_f32(int timestep_number0, int nrec, const float* lsm, const
 int sbd_get_edges_f32(float* mask, const float* ice, const float* land, int nx, int ny, int h, int swap,
                       uint8_t* m1)
 {
+  return sbd_get_edges_ex_f32(mask, ice, land, nx, ny, h, swap, m1, nullptr, nullptr);
+}
+
+int sbd_get_edges_ex_f32(float* mask, const float* ice, const float* land, int nx, int ny, int h, int swap,
+                         uint8_t* m1, float* px, float* py)
+{
   if (!mask || !ice || !land) return fail(SBD_EINVAL, "NULL argument");
   if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
   if (h < 1) return fail(SBD_EINVAL, "halo must be >= 1");
@@ -3615,10 +3660,13 @@ int sbd_get_edges_f32(float* mask, const float* ice, const float* land, int nx, 
   if ((rc = t.out(mask, nh * 4, true, &d_mask))) return rc;  // halos may be caller-initialised (swap==0)
   if ((rc = t.out(m1, n2, false, &d_m1))) return rc;
   if ((rc = t.scratch(n2 * 4, &d_coast))) return rc;
+  void *d_px, *d_py;
+  if ((rc = t.out(px, n2 * 4, false, &d_px))) return rc;
+  if ((rc = t.out(py, n2 * 4, false, &d_py))) return rc;
   dim3 g(cdiv(nx, 128), ny);
   k_binarise_generic<<<g, 128, 0, t.st>>>((float*)d_mask, d_ice, d_land, nx, ny, h, (uint8_t*)d_m1); LAUNCHED();
   if (swap && (rc = swap_bounds_dev(t.st, (float*)d_mask, nx, ny, h, true))) return rc;   // G:342
-  k_sobel_generic<<<g, 128, 0, t.st>>>((const float*)d_mask, (float*)d_coast, nx, ny, h); LAUNCHED();
+  k_sobel_generic<<<g, 128, 0, t.st>>>((const float*)d_mask, (float*)d_coast, nx, ny, h, (float*)d_px, (float*)d_py); LAUNCHED();
   k_copy_interior<<<g, 128, 0, t.st>>>((float*)d_mask, (const float*)d_coast, nx, ny, h); LAUNCHED();  // G:369
   if (swap && (rc = swap_bounds_dev(t.st, (float*)d_mask, nx, ny, h, true))) return rc;   // G:371
   CK(cudaGetLastError());

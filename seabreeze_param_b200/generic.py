@@ -31,17 +31,19 @@ def _chk(a, shape, name):
     return a
 
 
-def get_edges(mask, icefrac, landfrac, halo_size, swap=True, m1=None):
+def get_edges(mask, icefrac, landfrac, halo_size, swap=True, m1=None, px=None, py=None):
     """call get_edges(mask, icefrac, landfrac, halo_size)  (G:273-373).  mask (ny+2h, nx+2h) is
-    written in place: interior = coast flag, halos filled by swap_bounds when ``swap``."""
+    written in place: interior = coast flag, halos filled by swap_bounds when ``swap``.
+    Optional by-products: ``m1`` (uint8 (ny, nx)) the binarised mask, ``px``, ``py`` (float32 (ny, nx))
+    the Sobel components of G:350-357."""
     ny, nx = landfrac.shape
     h = int(halo_size)
     _chk(mask, (ny + 2 * h, nx + 2 * h), "mask")
     _chk(icefrac, (ny, nx), "icefrac")
     _chk(landfrac, (ny, nx), "landfrac")
     lib = _capi.load()
-    _capi.check(lib.sbd_get_edges_f32(_capi.ptr(mask), _capi.ptr(icefrac), _capi.ptr(landfrac), nx, ny, h,
-                                      1 if swap else 0, _capi.ptr(m1)), "get_edges")
+    _capi.check(lib.sbd_get_edges_ex_f32(_capi.ptr(mask), _capi.ptr(icefrac), _capi.ptr(landfrac), nx, ny, h,
+                                         1 if swap else 0, _capi.ptr(m1), _capi.ptr(px), _capi.ptr(py)), "get_edges")
     return mask
 
 
@@ -153,6 +155,13 @@ class Plan:
         """Overlap consecutive device-resident steps (inputs of a step must be complete before the
         previous step call is issued).  See sbd_plan_set_pipelined."""
         _capi.check(self.lib.sbd_plan_set_pipelined(self._h, 1 if on else 0), "plan_set_pipelined")
+
+    def window_info(self):
+        """(nn, n_land, n_sea): int32 (ny, nx) arrays -- the radius at which the growing-window loop
+        (G:188-214) stops for every cell and its land / sea counters; 0 outside the coastal zone."""
+        out = [np.zeros((self.ny, self.nx), dtype=np.int32) for _ in range(3)]
+        _capi.check(self.lib.sbd_plan_window_info(self._h, *[o.ctypes.data for o in out]), "plan_window_info")
+        return out
 
     def set_window_kernel(self, mode):
         """0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4).  See sbd_plan_set_window_kernel."""

@@ -367,6 +367,32 @@ def test_generic_pipelined_steps(oracle, name):
     plan.close()
 
 
+@pytest.mark.parametrize("name", ["t_gen", "c1"])
+def test_stencil_byproducts(oracle, name):
+    """the Sobel components px, py (G:350-357) out of get_edges, and out of the plan
+    the radius nn at which the growing-window loop (G:188-214) stops with its counters n_l, n_s."""
+    cfg = synth.CONFIGS[name]
+    case = generic_case(cfg, oracle)
+    ny, nx, h = cfg.ny, cfg.nx, cfg.h
+    # the binarised, halo-swapped mask the Sobel reads: rebuild it on the oracle side from m1
+    m1_h = synth.pad_halo(case["m1"].astype(np.float32), h)
+    oracle.swap_bounds(m1_h, h)
+    px_o, py_o = oracle.sobel(m1_h, h)
+    mask = np.zeros((ny + 2 * h, nx + 2 * h), np.float32)
+    px = np.full((ny, nx), 99.0, np.float32); py = np.full((ny, nx), 99.0, np.float32)
+    generic.get_edges(mask, case["ice"], case["land"], h, px=px, py=py)
+    assert_bits_equal(case["coast_h"], mask, "coast")
+    assert_bits_equal(px_o, px, "px"); assert_bits_equal(py_o, py, "py")
+    assert np.array_equal((px != 0) | (py != 0), mask[h:h + ny, h:h + nx] != 0)
+    plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, h)
+    plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
+    nn, nl, ns = plan.window_info()
+    nn_o, nl_o, ns_o = oracle.window_info(case["mask_h"], h)
+    assert np.array_equal(nn, nn_o) and np.array_equal(nl, nl_o) and np.array_equal(ns, ns_o)
+    assert nn.max() == plan.info()["nn_max"] and int((nn > 0).sum()) == plan.info()["n_coastal"]
+    plan.close()
+
+
 def test_generic_virtual_halo(oracle):
     """Plan halo mode 7: swap_bounds folded into the kernels' reads -- theta arrives with garbage in
     its halo and the result equals the run with explicitly filled halos."""

@@ -98,8 +98,8 @@ __device__ __forceinline__ int nbr_index(const Geo& g, int gx, int gy)
     int y = min(max(gy + g.h, 0), g.ldy - 1);
     return y * g.ldx + x;
   } else {
-    int m = (gx + 1) % g.nx;
-    if (m < 0) m += g.nx;
+    int m = gx + 1;  // modulo(jj, nlons), non-negative; the division only for offsets beyond one period
+    if (m < 0 || m >= g.nx) { m %= g.nx; if (m < 0) m += g.nx; }
     const int col = (m == 0) ? 0 : m - 1;
     const int row = min(max(gy, 0), g.ny - 1);
     return row * g.nx + col;
@@ -867,6 +867,7 @@ struct TrigArgs {
   // posts sync_seq into sync_up[1] and sync_dn[0].  Only CTAs that read neighbour rows wait.
   uint32_t* sync_local; uint32_t* sync_up; uint32_t* sync_dn;
   uint32_t sync_seq;
+  int strip_min;  // k_win4: smallest strip radius that is walked as a strip (>= 6); below, one cell per thread
 };
 
 // ---- peer flags over NVLink (system scope) ----
@@ -1680,7 +1681,7 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
     if (b & 0x40u) any_wide = true;
     if (nnq[q] > 0) { nn_w = max(nn_w, nnq[q]); nn_lo = min(nn_lo, nnq[q]); ++n_coast; }
   }
-  const bool as_strip = nn_w >= SMALL && n_coast >= 2 && nn_w - nn_lo <= 3;
+  const bool as_strip = nn_w >= a.strip_min && n_coast >= 2 && nn_w - nn_lo <= 3;
   int my_slot = -1;
   int cslot[CW];
   if (as_strip) my_slot = atomicAdd(&s_cnt[nn_w], 1);
@@ -2826,6 +2827,9 @@ int launch_win4(sbd_plan* p, TrigArgs& a)
   const int W = TX + 2 * R, Hh = TY + 2 * R;
   const int WP = W + ((17 - (W & 15)) & 15);
   const size_t smem = (size_t)WP * Hh * 8 + TX * TY + (size_t)(NT + TX * TY) * 4;
+  static int strip_min_env = -1;
+  if (strip_min_env < 0) { const char* e = getenv("SBD_STRIP_MIN"); strip_min_env = e ? atoi(e) : 0; }
+  a.strip_min = strip_min_env > 0 ? max(strip_min_env, 6) : 6;
   auto kern = k_win4<VARIANT, GEN>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));

@@ -1,2 +1,2 @@
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_win4 -s 6 -c 1 -o gpurun_out/prof_win4_c4 -f python scripts/probe_py.py c4 2 > gpurun_out/ncu_win4_c4.log 2>&1
-tail -2 gpurun_out/ncu_win4_c4.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1

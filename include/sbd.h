@@ -106,6 +106,29 @@ int sbd_seabreeze_diag_f32(float timestep, int timestep_number, const float* p, 
  * row blocks) lives in seabreeze_param_b200/halo.py and uses sbd_swap_bounds_ew_f32 for the local
  * periodic part. */
 int sbd_swap_bounds_f32(float* field, int nx, int ny, int h);
+
+/* ---- 64-bit REAL twins ------------------------------------------
+ * For hosts compiled with promoted reals (the UM's usual -r8 build: real(kind=jprb) at
+ * UM/vn10.7/sea_breeze_diag.F90:64).  Same arguments as the _f32 routines with double arrays and
+ * scalars (host or device pointers).  The arrays are narrowed to fp32 on the device (round to
+ * nearest), the fp32 kernels run unchanged, and the results are widened exactly, so
+ *   twin(x) == widen(f32 routine(narrow(x)))  bit for bit,
+ * and for inputs that are exactly representable in fp32 the twin reproduces the fp32 results.
+ * Against an evaluation that keeps 64 bits throughout, the floating-point diagnostics agree to
+ * fp32 accuracy (tests/test_gpu_f64.py: relative 2e-4 on sb_con, thc, windspeed; 2e-3 degrees on
+ * winddir) and the trigger flag can differ only where a quantity sits within fp32 rounding of its
+ * threshold.  No 64-bit arithmetic kernels exist in this round. */
+int sbd_get_edges_f64(double* mask, const double* icefrac, const double* landfrac, int nx, int ny, int h,
+                      int swap);
+int sbd_get_dist_f64(const double* coast, const double* landfrac, const double* lon, const double* lat,
+                     double maxdist, double* cdist, int nx, int ny, int h);
+int sbd_sigmoid_f64(const double* ary, double* sm, int nx, int ny);
+int sbd_seabreeze_diag_f64(double timestep, int timestep_number, const double* p, const double* u,
+                           const double* v, const double* theta, const double* mask, const double* z,
+                           const double* sigma, double* windspeed, double* winddir, double* thc,
+                           double* sb_con, int nx, int ny, int nz, int h, const sbd_params* prm,
+                           uint8_t* flags);
+int sbd_swap_bounds_f64(double* field, int nx, int ny, int h);
 int sbd_swap_bounds_ew_f32(float* field, int nx, int ny, int h);
 /* Asynchronous device-only form: one kernel on `stream` (cudaStream_t as void*).  ns_mask bit0 /
  * bit1: replicate the top / bottom edge rows (clear the bit for a side owned by a neighbour rank). */

@@ -2449,6 +2449,18 @@ struct ActiveFlag {
   }
 };
 
+// 64-bit <-> 32-bit REAL conversion for the _f64 twins of the C-ABI (round to nearest / exact widening)
+__global__ void k_narrow(const double* __restrict__ src, float* __restrict__ dst, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+__global__ void k_widen(const float* __restrict__ src, double* __restrict__ dst, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+
 }  // namespace sbdk
 using namespace sbdk;
 
@@ -3816,6 +3828,146 @@ int sbd_stats_chain_f32(const float* ary, int nx, int ny, int ld, int pass, int 
   launch_stats_pass(t.st, d_ary, nx, ny, ld, pass, first, (float*)d_carry);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(carry5, d_carry, 20, cudaMemcpyDeviceToHost, t.st));
+  return t.finish();
+}
+
+// ------------------------------------------------------------------------------------------------
+// _f64 twins: hosts built with promoted 64-bit REALs (UM -r8).  The arrays are
+// narrowed to fp32 on the device (round to nearest), the fp32 kernels run unchanged, results are
+// widened exactly.  See include/sbd.h for what that means against a true 64-bit evaluation.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Tmp64 {
+  cudaStream_t st = nullptr;
+  std::vector<void*> bufs;
+  struct Out { double* user; float* d32; size_t n; };
+  std::vector<Out> outs;
+  ~Tmp64() { for (void* b : bufs) cudaFree(b); }
+  int alloc(size_t bytes, void** d) { CK(cudaMalloc(d, bytes)); bufs.push_back(*d); return SBD_OK; }
+  // fp32 device copy of a 64-bit array that lives on the host or on the device
+  int in(const double* src, size_t n, float** out)
+  {
+    const double* d64 = src;
+    if (!is_device_ptr(src)) {
+      void* d; int rc = alloc(n * 8, &d); if (rc) return rc;
+      CK(cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, st));
+      d64 = (const double*)d;
+    }
+    void* d32; int rc = alloc(n * 4, &d32); if (rc) return rc;
+    k_narrow<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d64, (float*)d32, (long long)n); LAUNCHED();
+    *out = (float*)d32;
+    return SBD_OK;
+  }
+  // fp32 device buffer standing in for a 64-bit output (copy_in: the routine also reads it)
+  int out(double* dst, size_t n, bool copy_in, float** o)
+  {
+    int rc;
+    if (copy_in) { if ((rc = in(dst, n, o))) return rc; }
+    else { void* d32; if ((rc = alloc(n * 4, &d32))) return rc; *o = (float*)d32; }
+    outs.push_back({dst, *o, n});
+    return SBD_OK;
+  }
+  int finish()
+  {
+    for (auto& o : outs) {
+      if (is_device_ptr(o.user)) {
+        k_widen<<<(unsigned)((o.n + 255) / 256), 256, 0, st>>>(o.d32, o.user, (long long)o.n); LAUNCHED();
+      } else {
+        void* d64; int rc = alloc(o.n * 8, &d64); if (rc) return rc;
+        k_widen<<<(unsigned)((o.n + 255) / 256), 256, 0, st>>>(o.d32, (double*)d64, (long long)o.n); LAUNCHED();
+        CK(cudaMemcpyAsync(o.user, d64, o.n * 8, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return SBD_OK;
+  }
+};
+}  // namespace
+
+int sbd_get_edges_f64(double* mask, const double* ice, const double* land, int nx, int ny, int h, int swap)
+{
+  if (!mask || !ice || !land) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  if (h < 1) return fail(SBD_EINVAL, "halo must be >= 1");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp64 t;
+  const size_t n2 = (size_t)nx * ny, nh = (size_t)(nx + 2 * h) * (ny + 2 * h);
+  float *d_mask, *d_ice, *d_land;
+  if ((rc = t.in(ice, n2, &d_ice)) || (rc = t.in(land, n2, &d_land)) || (rc = t.out(mask, nh, true, &d_mask))) return rc;
+  CK(cudaStreamSynchronize(t.st));
+  if ((rc = sbd_get_edges_f32(d_mask, d_ice, d_land, nx, ny, h, swap, nullptr))) return rc;
+  return t.finish();
+}
+
+int sbd_get_dist_f64(const double* coast, const double* land, const double* lon, const double* lat,
+                     double maxdist, double* cdist, int nx, int ny, int h)
+{
+  if (!coast || !land || !lon || !lat || !cdist) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  if (h < 0) return fail(SBD_EINVAL, "bad halo");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp64 t;
+  const size_t n2 = (size_t)nx * ny, nh = (size_t)(nx + 2 * h) * (ny + 2 * h);
+  float *d_coast, *d_land, *d_lon, *d_lat, *d_cd;
+  if ((rc = t.in(coast, nh, &d_coast)) || (rc = t.in(land, n2, &d_land)) || (rc = t.in(lon, nx, &d_lon)) ||
+      (rc = t.in(lat, ny, &d_lat)) || (rc = t.out(cdist, n2, false, &d_cd))) return rc;
+  CK(cudaStreamSynchronize(t.st));
+  if ((rc = sbd_get_dist_f32(d_coast, d_land, d_lon, d_lat, (float)maxdist, d_cd, nx, ny, h))) return rc;
+  return t.finish();
+}
+
+int sbd_sigmoid_f64(const double* ary, double* sm, int nx, int ny)
+{
+  if (!ary || !sm) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp64 t;
+  const size_t n2 = (size_t)nx * ny;
+  float *d_ary, *d_sm;
+  if ((rc = t.in(ary, n2, &d_ary)) || (rc = t.out(sm, n2, false, &d_sm))) return rc;
+  CK(cudaStreamSynchronize(t.st));
+  if ((rc = sbd_sigmoid_f32(d_ary, d_sm, nx, ny, nullptr))) return rc;
+  return t.finish();
+}
+
+int sbd_swap_bounds_f64(double* field, int nx, int ny, int h)
+{
+  if (!field || nx < 1 || ny < 1 || h < 0) return fail(SBD_EINVAL, "bad argument");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp64 t;
+  float* d_f;
+  if ((rc = t.out(field, (size_t)(nx + 2 * h) * (ny + 2 * h), true, &d_f))) return rc;
+  CK(cudaStreamSynchronize(t.st));
+  if ((rc = sbd_swap_bounds_f32(d_f, nx, ny, h))) return rc;
+  return t.finish();
+}
+
+int sbd_seabreeze_diag_f64(double timestep, int step, const double* pp, const double* u, const double* v,
+                           const double* theta, const double* mask, const double* z, const double* sigma,
+                           double* ws, double* wd, double* thc, double* sb, int nx, int ny, int nz, int h,
+                           const sbd_params* prm, uint8_t* flags)
+{
+  if (!pp || !u || !v || !theta || !mask || !z || !sigma || !ws || !wd || !thc || !sb)
+    return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1 || nz < 1) return fail(SBD_EDIMS, "bad dims");   // U:198-201 -> error = 1
+  if (h < 0) return fail(SBD_EINVAL, "bad halo");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp64 t;
+  const size_t n2 = (size_t)nx * ny, n3 = n2 * nz, nh = (size_t)(nx + 2 * h) * (ny + 2 * h);
+  float *d_p, *d_u, *d_v, *d_th, *d_mk, *d_z, *d_sg, *d_ws, *d_wd, *d_thc, *d_sb;
+  if ((rc = t.in(pp, n3, &d_p)) || (rc = t.in(u, n3, &d_u)) || (rc = t.in(v, n3, &d_v)) ||
+      (rc = t.in(theta, nh, &d_th)) || (rc = t.in(mask, nh, &d_mk)) || (rc = t.in(z, nh, &d_z)) ||
+      (rc = t.in(sigma, nh, &d_sg)) || (rc = t.out(ws, n2, true, &d_ws)) || (rc = t.out(wd, n2, true, &d_wd)) ||
+      (rc = t.out(thc, n2, true, &d_thc)) || (rc = t.out(sb, n2, true, &d_sb))) return rc;
+  CK(cudaStreamSynchronize(t.st));
+  if ((rc = sbd_seabreeze_diag_f32((float)timestep, step, d_p, d_u, d_v, d_th, d_mk, d_z, d_sg, d_ws, d_wd, d_thc,
+                                   d_sb, nx, ny, nz, h, prm, flags))) return rc;
   return t.finish();
 }
 

@@ -15,7 +15,7 @@
 ! Keyword calls are order-agnostic either way (SURVEY.md A.6).
 !
 ! Default REAL must be 32-bit (c_float).  A UM build with promoted reals (-r8)
-! needs the _f64 twins of the C-ABI (SURVEY.md section 8f, not in this round).
+! uses sea_breeze_diag_mod_r8.f90 (the _f64 twins of the C-ABI) instead of this file.
 !
 ! NOTE: no Fortran compiler exists in the build image of this repository, so
 ! this file is compiled by the integrator, not by the test-suite; the same

@@ -139,3 +139,30 @@ def test_sigmoid_sequential_order(oracle):
     assert st[1] == np.float32(np.float32(2.0) / np.sqrt(np.float32(var / np.float32(a.size))))
     assert st[2] == np.float32((a.max() - a.min()) / np.float32(4.0))
     assert 0 < sm.min() and sm.max() <= 1
+
+
+def test_byproducts_known_answers(oracle):
+    """orc_sobel / orc_window_info on hand-checkable cases."""
+    h = 2
+    # meridional coastline: land for x >= 4 in an 8 x 6 grid (halo filled by swap_bounds: E-W periodic)
+    m = np.zeros((6, 8), np.float32); m[:, 4:] = 1.0
+    mh = np.zeros((6 + 2 * h, 8 + 2 * h), np.float32); mh[h:-h, h:-h] = m
+    oracle.swap_bounds(mh, h)
+    px, py = oracle.sobel(mh, h)
+    assert np.all(py == 0.0)                       # no north-south gradient
+    assert np.all(px[:, 3] == 4.0) and np.all(px[:, 4] == 4.0)     # (1+2+1) * (1 - 0) on both coast columns
+    assert np.all(px[:, 1:3] == 0.0) and np.all(px[:, 5:7] == 0.0)
+    assert np.all(px[:, 0] == -4.0) and np.all(px[:, 7] == -4.0)   # the periodic seam is a coastline too
+    # signed distance plane: sea (-) left of x = 4, land (+) right; everything inside maxdist
+    cd = np.where(m > 0, 10.0, -10.0).astype(np.float32)
+    ch = np.zeros_like(mh); ch[h:-h, h:-h] = cd
+    oracle.swap_bounds(ch, h)
+    nn, nl, ns = oracle.window_info(ch, h)
+    assert np.all(nn[:, 3] == 1) and np.all(nn[:, 4] == 1)         # next to the coast: 3 x 3 window suffices
+    assert np.all(nl[:, 3] == 3) and np.all(ns[:, 3] == 6) and np.all(nl[:, 4] == 6) and np.all(ns[:, 4] == 3)
+    assert np.all(nn[:, 2] == 2) and np.all(nl[:, 2] == 5) and np.all(ns[:, 2] == 20)   # 5 x 5: one land column
+    assert np.all((nl + ns) == (2 * nn + 1) ** 2)
+    # cells beyond maxdist are skipped (G:174-176)
+    ch2 = ch.copy(); ch2[h:-h, h:h + 2] = -500.0
+    nn2, nl2, ns2 = oracle.window_info(ch2, h)
+    assert np.all(nn2[:, :2] == 0) and np.all(nl2[:, :2] == 0) and np.all(ns2[:, :2] == 0)

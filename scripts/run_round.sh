@@ -1,4 +1,4 @@
-python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"
-python -c "
-import json
-d=json.load(open('gpurun_out/bench_final.json')); print(d['ms_per_step'], d['value'], d['steps'], d['e2e']['ms_per_step'], d['cpu_baseline']['ms_per_step'], d['roofline']['frac'], d['clocks'])"
+for kb in 0 44 56 75; do
+  echo "== TRIG_SMEM_KB=$kb"
+  SBD_TRIG_SMEM_KB=$kb PROBE_FLAGS=1 timeout 120 python scripts/probe_step.py c2 2>&1 | grep -E "wall|per-kernel" | cut -c1-120
+done

@@ -231,6 +231,14 @@ int sbd_plan_set_pipelined(sbd_plan* plan, int on);
  * 2 = strip kernel (four cells per thread share every shared-memory load, packed fp32 adds).
  * Both evaluate each cell's sums in the reference's raster order: identical bits. */
 int sbd_plan_set_window_kernel(sbd_plan* plan, int mode);
+/* Restrict the trigger to rows [row_lo, row_hi) of the plan's grid (row_hi < 0: to the end); call before
+ * sbd_plan_set_static.  Cells of other rows are treated like cells outside the coastal zone (missing
+ * value, state untouched) but still serve as neighbours.  This is how the python variant -- whose
+ * index map clamps rows at the array edge -- is sharded over GPUs without any exchange: a rank's plan
+ * holds its rows plus an overlap of >= the largest search radius on either side and processes only its
+ * own rows (seabreeze_param_b200/halo.py: PyRowBlock).  The python variant's "last row is never
+ * processed" (seabreeze_diag_python.f90:165) still applies to the plan's last row. */
+int sbd_plan_set_row_window(sbd_plan* plan, int row_lo, int row_hi);
 /* Process-wide default for plans left at mode 0 (also used by the one-shot entry points). */
 int sbd_set_window_kernel_default(int mode);
 /* Static fields: mask = signed coast distance, z, sigma (generic: halo'd; python: nlons x nlats).

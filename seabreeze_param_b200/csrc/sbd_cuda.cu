@@ -761,7 +761,7 @@ __global__ void k_static_gzsm(const float* __restrict__ z, const float* __restri
 
 template <int VARIANT>
 __global__ void k_static_code(const float* __restrict__ mask, uint16_t* __restrict__ code, Geo g,
-                              float maxdist, int nncap, int rows_processed, int* __restrict__ nn_max,
+                              float maxdist, int nncap, int row_lo, int rows_processed, int* __restrict__ nn_max,
                               int* __restrict__ n_coastal)
 {
   const int px = blockIdx.x * blockDim.x + threadIdx.x;  // plane coordinates
@@ -771,7 +771,7 @@ __global__ void k_static_code(const float* __restrict__ mask, uint16_t* __restri
   const float m = mask[s];
   uint32_t c = (m >= 0.0f) ? 0x8000u : 0u;
   const int gx = px - g.h, gy = py - g.h;
-  const bool interior = gx >= 0 && gx < g.nx && gy >= 0 && gy < rows_processed;
+  const bool interior = gx >= 0 && gx < g.nx && gy >= row_lo && gy < rows_processed;
   if (interior && !(fabsf(m) > maxdist)) {
     bool hl = false, hs = false;
     int nn = 1;
@@ -2476,6 +2476,7 @@ struct sbd_plan {
   float* d_gzsm = nullptr;
   uint16_t* d_code = nullptr;
   uint32_t* d_cl = nullptr;   // land cells in every coastal-zone cell's final window (k_static_counts)
+  int row_lo = 0, row_hi = -1;  // sbd_plan_set_row_window (-1: to the end)
   int window_kernel = 0;      // sbd_plan_set_window_kernel: 0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4)
   float* d_stats = nullptr;   // 4 floats
   float* d_carry = nullptr;   // 5 floats
@@ -3068,6 +3069,13 @@ int sbd_plan_set_peer_sync(sbd_plan* p, uint32_t* sync_local, uint32_t* sync_up,
   p->sync_seq = 0;
   return SBD_OK;
 }
+int sbd_plan_set_row_window(sbd_plan* p, int row_lo, int row_hi)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  if (row_lo < 0 || (row_hi >= 0 && row_hi < row_lo) || row_hi > p->ny) return fail(SBD_EINVAL, "bad row window");
+  p->row_lo = row_lo; p->row_hi = row_hi;
+  return SBD_OK;
+}
 int sbd_set_window_kernel_default(int mode)
 {
   if (mode < 0 || mode > 2) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 strips");
@@ -3155,12 +3163,17 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
   cudaStream_t st = p->stream;
   CK(cudaMemsetAsync(p->d_cnt, 0, 4 * sizeof(int), st));
   dim3 grid(cdiv(p->g.ldx, 128), p->g.ldy);
+  // rows that get a search radius at all: the whole block, minus the last row for the python variant
+  // (P:165), intersected with sbd_plan_set_row_window
+  const int row_lo = max(p->row_lo, 0);
+  const int row_end = (p->variant == SBD_VARIANT_GENERIC) ? p->ny : p->ny - 1;
+  const int row_hi = (p->row_hi >= 0) ? min(p->row_hi, row_end) : row_end;
   if (p->variant == SBD_VARIANT_GENERIC) {
     k_static_code<SBD_VARIANT_GENERIC><<<grid, 128, 0, st>>>(d_mask, p->d_code, p->g, p->prm.maxdist,
-                                                            max(p->h, 1), p->ny, p->d_cnt, p->d_cnt + 1);
+                                                            max(p->h, 1), row_lo, row_hi, p->d_cnt, p->d_cnt + 1);
   } else {
     k_static_code<SBD_VARIANT_PYTHON><<<grid, 128, 0, st>>>(d_mask, p->d_code, p->g, p->prm.maxdist,
-                                                           max(p->nx, p->ny), p->ny - 1, p->d_cnt, p->d_cnt + 1);
+                                                           max(p->nx, p->ny), row_lo, row_hi, p->d_cnt, p->d_cnt + 1);
   }
   LAUNCHED();
   {

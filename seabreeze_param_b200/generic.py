@@ -163,6 +163,10 @@ class Plan:
         _capi.check(self.lib.sbd_plan_window_info(self._h, *[o.ctypes.data for o in out]), "plan_window_info")
         return out
 
+    def set_row_window(self, row_lo, row_hi=-1):
+        """Process only rows [row_lo, row_hi) (before set_static).  See sbd_plan_set_row_window."""
+        _capi.check(self.lib.sbd_plan_set_row_window(self._h, int(row_lo), int(row_hi)), "plan_set_row_window")
+
     def set_window_kernel(self, mode):
         """0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4).  See sbd_plan_set_window_kernel."""
         _capi.check(self.lib.sbd_plan_set_window_kernel(self._h, int(mode)), "plan_set_window_kernel")

@@ -180,3 +180,57 @@ class PeerHalo:
 
     def barrier(self):
         self.hdl.barrier(channel=0)
+
+
+class PyRowBlock:
+    """Row-block sharding of the PYTHON variant (diag, seabreeze_diag_python.f90:49-285) -- no exchange at all.
+
+    The python variant has no halos: its index map clamps rows at the array edge (P:201) and wraps
+    columns (P:202).  A rank that owns rows [r0, r1) of the (nlats, nlons) grid therefore builds its
+    plan on rows [a, b) = [max(0, r0 - overlap), min(nlats, r1 + overlap)) of every 2-D field and
+    restricts the trigger to its own rows (Plan.set_row_window): with overlap >= the largest search
+    radius no owned cell's window ever reaches the block's edge, except where that edge is the
+    domain's own edge and clamps exactly as the single-domain run does.  The sigmoid statistics are
+    taken from the whole grid (sequential order), the rule "the last row is never processed"
+    (P:165) falls on the global last row because only the last block contains it.  Per record each
+    rank reads its rows (+ overlap) of theta, u, v from the input files on its own: the path shards
+    with overlapping reads and no collective (config c4 of BASELINE.json).
+    """
+
+    def __init__(self, nlons, nlats, nps, rank, world, cdist, z, std, overlap, params=None, device=None):
+        """cdist, z, std: the GLOBAL (nlats, nlons) float32 fields (numpy, C order == Fortran (nlons, nlats));
+        overlap: rows read beyond the owned block, >= the largest search radius (<= k + 1, k the
+        get_dist radius; `required_overlap` checks it after the fact)."""
+        from . import generic
+        self.nx, self.ny, self.nz = nlons, nlats, nps
+        self.rank, self.world = rank, world
+        per = (nlats + world - 1) // world
+        self.r0, self.r1 = min(rank * per, nlats), min((rank + 1) * per, nlats)
+        self.a, self.b = max(0, self.r0 - overlap), min(nlats, self.r1 + overlap)
+        self.overlap = overlap
+        # global sequential statistics of std (P:291-309) -- static, every rank computes the same bits
+        st = np.zeros(4, dtype=np.float32)
+        generic.sigmoid(np.ascontiguousarray(std, dtype=np.float32), stats=st)
+        self.stats = st[:3].copy()
+        self.plan = generic.Plan(generic.SBD_VARIANT_PYTHON, nlons, self.b - self.a, nps, params=params)
+        self.plan.set_row_window(self.r0 - self.a, self.r1 - self.a)
+        cut = lambda f: np.ascontiguousarray(f[self.a:self.b], dtype=np.float32)
+        self.plan.set_static(cut(cdist), cut(z), cut(std), stats=self.stats)
+
+    def required_overlap(self):
+        """Largest search radius among the owned cells; the overlap must not be smaller."""
+        return self.plan.info()["nn_max"]
+
+    def rows(self):
+        """(a, b): the rows of the global 2-D fields this rank has to read per record."""
+        return self.a, self.b
+
+    def step(self, timestep_number, timestep_min, p, u_blk, v_blk, theta_blk, ws_blk, wd_blk, flags=None):
+        """One record.  u_blk, v_blk: (nps, b-a, nlons); theta_blk, ws_blk, wd_blk: (b-a, nlons) -- rows
+        [a, b) of the global arrays.  Returns (sb_con, t0, windspeed, winddir) for the OWNED rows
+        [r0, r1) only, each (r1-r0, nlons)."""
+        nb = self.b - self.a
+        out = np.zeros((4, nb, self.nx), dtype=np.float32)
+        self.plan.step_py(timestep_number, timestep_min, p, u_blk, v_blk, theta_blk, ws_blk, wd_blk, out, flags=flags)
+        lo, hi = self.r0 - self.a, self.r1 - self.a
+        return tuple(out[k, lo:hi] for k in range(4))

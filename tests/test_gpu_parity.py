@@ -156,6 +156,51 @@ def test_py_diag_mid_radius(oracle, wk):
             ws_g, wd_g = np.ascontiguousarray(gc[2]), np.ascontiguousarray(gc[3])
 
 
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["t_py", "t_py_mid"])
+def test_py_row_blocks_no_exchange(oracle, name, world):
+    """The python variant sharded into overlapping row blocks (halo.PyRowBlock, one plan per rank, no
+    exchange): the ranks' owned rows, stitched together, equal the oracle's single-domain result bit
+    for bit -- all four output planes, three records with the state threaded through.  The ranks run
+    one after the other on this GPU; nothing they compute depends on another rank."""
+    from seabreeze_param_b200 import halo
+    cfg = synth.CONFIGS[name] if name in synth.CONFIGS else synth.Config(
+        "t_py_mid", 720, 361, 9, 0, "python", 10.0, False, 60.0, "0.5 degree python-variant test")
+    land, ice, lon, lat, z, sig = synth.static_fields(cfg)
+    coast = oracle.py_get_edges(land, ice)
+    cd = oracle.py_get_dist(coast, land, lon, lat, literal=False)
+    ny, nx = cfg.ny, cfg.nx
+    probe = generic.Plan(SBD_VARIANT_PYTHON, nx, ny, cfg.nz)
+    probe.set_static(cd, z, sig)
+    overlap = probe.info()["nn_max"]
+    probe.close()
+    blocks = [halo.PyRowBlock(nx, ny, cfg.nz, r, world, cd, z, sig, overlap) for r in range(world)]
+    assert all(b.required_overlap() <= overlap for b in blocks)
+    assert blocks[0].r0 == 0 and blocks[-1].r1 == ny and all(blocks[i].r1 == blocks[i + 1].r0 for i in range(world - 1))
+    ws_o = np.zeros_like(z); wd_o = np.zeros_like(z)
+    ws_g = np.zeros_like(z); wd_g = np.zeros_like(z)
+    for step in (1, 2, 6):
+        theta, p, u, v = synth.step_fields(cfg, step, land, z, lat)
+        o, f = oracle.py_diag(step, p, z, sig, theta, v, u, cd, ws_o, wd_o, timestep=cfg.timestep, literal=True)
+        got = np.zeros((4, ny, nx), np.float32)
+        fl = np.zeros((ny, nx), np.uint8)
+        for b in blocks:
+            a_, b_ = b.rows()
+            c = lambda x: np.ascontiguousarray(x[..., a_:b_, :])
+            fb = np.zeros((b_ - a_, nx), np.uint8)
+            res = b.step(step, cfg.timestep, p, c(u), c(v), c(theta), c(ws_g), c(wd_g), flags=fb)
+            for k in range(4):
+                got[k, b.r0:b.r1] = res[k]
+            fl[b.r0:b.r1] = fb[b.r0 - a_:b.r1 - a_]
+        for k, nm in enumerate(("sb_con", "t0", "windspeed", "winddir")):
+            assert_bits_equal(o[k], got[k], "%s step %d (%d row blocks)" % (nm, step, world))
+        assert np.array_equal(f, fl), "flags step %d" % step
+        ws_o, wd_o = o[2].copy(), o[3].copy()
+        ws_g, wd_g = got[2].copy(), got[3].copy()
+    for b in blocks:
+        b.plan.close()
+
+
 def test_py_wrapper_diag_matches_manual_loop(oracle):
     """seabreezediag.diag (mirror of the reference's Python API) == the same loop done by hand on
     the oracle, including get_edges/get_dist per record with time-varying ice."""

@@ -5,16 +5,21 @@ A "step" is one call of seabreeze_diag (generic/sea_breeze_diag.f90:55-271) over
 synthetic fields on the N512-class grid of BASELINE.json configs[1] (1024 x 769 x 70, halo 6).
 
   value      device-resident: inputs already in HBM, plan API (static fields processed once per
-             plan), K steps back to back over rotating input sets (> L2), CUDA events.
+             plan), K steps back to back over rotating input sets (> L2), CUDA
+             events on the launching stream around the whole timed region.
   e2e        the same step through the public host-buffer API (numpy arrays in pinned memory):
-             H2D of p,u,v,theta,state + kernel + D2H of state/sb_con inside the timed region.
-  roofline   k_trigger: algorithmic bytes 20N + nC(4nz+24) / measured launch time,
-             against MEASURED_PEAKS.json hbm_gbs.
+             H2D of p,u,v,theta,state + kernels + D2H of state/sb_con/flags inside the timed region.
+  roofline   the dominant kernel, the level scan k_scan_quad_regs: its algorithmic bytes nC (4 nz + 28)
+             (its share of B_diag = 20N + nC(4nz+24)) / its launch time measured with
+             CUDA events by the library, against MEASURED_PEAKS.json hbm_gbs; traffic = DRAM bytes per
+             launch from the committed ncu launch list (profiles/traffic_k_scan_quad_regs.json).
   cpu_baseline  the oracle (C++ restatement of the Fortran; gfortran does not exist here), literal
-             mode, on the host cores.
+             loops, platform libm, all host threads, full c2 grid, best of 3 steps.
 
-N > 1 (torchrun): weak scaling -- every rank owns one N512-sized latitude block of a taller grid,
-theta halo rows are exchanged with NCCL send/recv every step (seabreeze_param_b200/halo.py).
+N > 1 (torchrun): weak scaling -- every rank owns one N512-sized latitude block of a taller grid; the
+halo rows of theta are read from the neighbour ranks' planes over NVLink (symmetric memory) with the
+per-step handshake inside the window kernel (BENCH_PEER_SYNC=barrier: a barrier launch per step;
+BENCH_HALO=nccl: NCCL send/recv beside the level scan).  See seabreeze_param_b200/halo.py.
 
 --impl reference: times the oracle (kind "port") on the host cores for the same config.
 """

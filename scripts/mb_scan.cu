@@ -82,6 +82,42 @@ __global__ void __launch_bounds__(NT) scan_levelmajor(const float* __restrict__ 
   for (int q = 0; q < QPT; ++q) { const int i = base + q * NT; if (i < nq) out[i] = l[q]; }
 }
 
+// level split: S threads per quad, each scanning nz/S levels (B loads in flight each), combined by shuffle
+template <int B, int S, int NT>
+__global__ void __launch_bounds__(NT) scan_split(const float* __restrict__ p, const int* __restrict__ quads, int nq, size_t n2, int nz, float tp, int* __restrict__ out)
+{
+  // lanes: within a warp, lanes [0, 32/S) take part 0, the next 32/S part 1, ...: every part reads 32/S consecutive quads
+  const int QW = 32 / S;
+  const int warp = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int part = lane / QW, ql = lane % QW;
+  const int i = min(warp * QW + ql, nq - 1);
+  const int m = quads[i]; const size_t stride4 = n2 >> 2;
+  const float4* pq = reinterpret_cast<const float4*>(p) + m;
+  const int per = (nz + S - 1) / S, ka = part * per, kb = min(nz, ka + per);
+  float b0=3e38f,b1=3e38f,b2=3e38f,b3=3e38f; int l0=0,l1=0,l2=0,l3=0;
+  for (int k0 = ka; k0 < kb; k0 += B) {
+    float4 d[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) { const int kk = min(k0 + j, kb - 1);
+      asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(d[j].x),"=f"(d[j].y),"=f"(d[j].z),"=f"(d[j].w) : "l"(pq + (size_t)kk * stride4)); }
+#pragma unroll
+    for (int j = 0; j < B; ++j) { const int kk = k0 + j;
+        const float e0=fabsf(d[j].x-tp),e1=fabsf(d[j].y-tp),e2=fabsf(d[j].z-tp),e3=fabsf(d[j].w-tp);
+        if (kk<kb&&e0<b0){b0=e0;l0=kk;} if (kk<kb&&e1<b1){b1=e1;l1=kk;} if (kk<kb&&e2<b2){b2=e2;l2=kk;} if (kk<kb&&e3<b3){b3=e3;l3=kk;} }
+  }
+  // combine: strict < keeps the earlier part on ties (first minimum)
+#pragma unroll
+  for (int s = 1; s < S; s <<= 1) {
+    const int src = lane + s * QW;
+    float o; int ol;
+    o = __shfl_sync(0xffffffffu, b0, src); ol = __shfl_sync(0xffffffffu, l0, src); if (o < b0) { b0 = o; l0 = ol; }
+    o = __shfl_sync(0xffffffffu, b1, src); ol = __shfl_sync(0xffffffffu, l1, src); if (o < b1) { b1 = o; l1 = ol; }
+    o = __shfl_sync(0xffffffffu, b2, src); ol = __shfl_sync(0xffffffffu, l2, src); if (o < b2) { b2 = o; l2 = ol; }
+    o = __shfl_sync(0xffffffffu, b3, src); ol = __shfl_sync(0xffffffffu, l3, src); if (o < b3) { b3 = o; l3 = ol; }
+  }
+  if (part == 0 && warp * QW + ql < nq) out[i] = l0 + l1 + l2 + l3;
+}
+
 __global__ void copy_k(const float4* __restrict__ a, float4* __restrict__ b, size_t n) { size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x; size_t st=(size_t)gridDim.x*blockDim.x; for(;i<n;i+=st) b[i]=a[i]; }
 __global__ void read_k(const float4* __restrict__ a, float* __restrict__ o, size_t n) { size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x; size_t st=(size_t)gridDim.x*blockDim.x; float s=0; for(;i<n;i+=st){float4 v=__ldcs(a+i); s+=v.x+v.y+v.z+v.w;} if (s==123.456f) o[0]=s; }
 
@@ -128,5 +164,21 @@ int main(int argc, char** argv)
   RUN_RG(10,128,dd,nd,bd,"dense"); RUN_RG(10,128,dq,nq,bq,"frag "); RUN_RG(14,128,dq,nq,bq,"frag ");
 #define RUN_LM(Q,NT,list,n,bytes,tag) timeit(tag " levelmajor QPT=" #Q " NT=" #NT, [&](float* pp){ scan_levelmajor<Q,NT><<<(n+NT*Q-1)/(NT*Q),NT>>>(pp,list,n,n2,nz,70000.f,out); }, bytes);
   RUN_LM(1,256,dq,nq,bq,"frag ");
+  RUN_RG(5,128,dq,nq,bq,"frag "); RUN_RG(7,128,dq,nq,bq,"frag "); RUN_RG(7,64,dq,nq,bq,"frag "); RUN_RG(7,256,dq,nq,bq,"frag "); RUN_RG(14,256,dq,nq,bq,"frag "); RUN_RG(18,128,dq,nq,bq,"frag ");
+#define RUN_SP(B,S,NT,list,n,bytes,tag) timeit(tag " split B=" #B " S=" #S " NT=" #NT, [&](float* pp){ scan_split<B,S,NT><<<((n+(32/S)-1)/(32/S)*32+NT-1)/NT,NT>>>(pp,list,n,n2,nz,70000.f,out); }, bytes);
+  RUN_SP(5,2,128,dq,nq,bq,"frag "); RUN_SP(9,2,128,dq,nq,bq,"frag "); RUN_SP(6,4,128,dq,nq,bq,"frag "); RUN_SP(9,4,128,dq,nq,bq,"frag "); RUN_SP(9,2,256,dq,nq,bq,"frag "); RUN_SP(9,8,128,dq,nq,bq,"frag ");
+  // coarser fetch granules: every quad of each 64/128/256/512-byte block that holds an active cell
+  for (int gcells : {16, 32, 64, 128}) {
+    std::vector<int> ql; std::vector<uint8_t> blk(n2 / gcells + 1, 0);
+    for (size_t c = 0; c < n2; ++c) if (act[c]) blk[c / gcells] = 1;
+    for (size_t m = 0; m < n2 / 4; ++m) if (blk[(m * 4) / gcells]) ql.push_back((int)m);
+    int* dl; CK(cudaMalloc(&dl, ql.size() * 4)); CK(cudaMemcpy(dl, ql.data(), ql.size() * 4, cudaMemcpyHostToDevice));
+    const int nl = (int)ql.size(); const double bl = nl * 16.0 * nz;
+    char tag[64]; snprintf(tag, sizeof tag, "gran %4d B (%.1f MB) regs B=10", gcells * 4, bl / 1e6);
+    timeit(tag, [&](float* pp){ scan_regs<10,128><<<(nl+127)/128,128>>>(pp,dl,nl,n2,nz,70000.f,out); }, bl);
+    snprintf(tag, sizeof tag, "gran %4d B (%.1f MB) split B=9 S=2", gcells * 4, bl / 1e6);
+    timeit(tag, [&](float* pp){ scan_split<9,2,128><<<((nl+15)/16*32+127)/128,128>>>(pp,dl,nl,n2,nz,70000.f,out); }, bl);
+    cudaFree(dl);
+  }
   return 0;
 }

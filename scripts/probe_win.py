@@ -1,0 +1,84 @@
+"""Timing probe of the generic plan step on a named config with device-generated 3-D fields (2-D fields from
+synth, so masks / radii are the benchmark's): per-kernel times of every window-kernel form.
+usage: probe_win.py <cfg> [modes e.g. 3,2] [nz override]"""
+import sys, os, time, math
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from seabreeze_param_b200 import generic, synth
+from seabreeze_param_b200._capi import SBD_VARIANT_GENERIC, SBD_VARIANT_PYTHON
+
+name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+modes = [int(m) for m in (sys.argv[2] if len(sys.argv) > 2 else "3,2").split(",")]
+cfg = synth.CONFIGS[name]
+nz = int(sys.argv[3]) if len(sys.argv) > 3 else cfg.nz
+dev = torch.device("cuda:0")
+h, nx, ny = cfg.h, cfg.nx, cfg.ny
+land, ice, lon, lat, z, sig = synth.static_fields(cfg)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+g = torch.Generator(device=dev); g.manual_seed(1)
+latr = torch.deg2rad(t(lat).double())[:, None]
+theta = (300.0 - 30.0 * torch.sin(latr) ** 2 + 3.0 * t(land).double() + 0.5 * torch.randn((ny, nx), generator=g, device=dev, dtype=torch.float64)).float()
+u = 6.0 * torch.randn((nz, ny, nx), generator=g, device=dev)
+v = 6.0 * torch.randn((nz, ny, nx), generator=g, device=dev)
+flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+if cfg.variant == "generic":
+    k = torch.arange(nz, device=dev, dtype=torch.float32)[:, None, None]
+    p = (101325.0 * torch.exp(-t(z) / 8000.0)[None] * torch.exp(-k * math.log(100.0) / max(nz - 1, 1))).contiguous()
+    mask_h = torch.zeros((ny + 2 * h, nx + 2 * h), dtype=torch.float32, device=dev)
+    generic.get_edges(mask_h, t(ice), t(land), h)
+    cdist = torch.empty((ny, nx), dtype=torch.float32, device=dev)
+    generic.get_dist(mask_h, t(land), t(lon), t(lat), 180.0, cdist, h)
+    def haloed(a2d):
+        f = torch.zeros((ny + 2 * h, nx + 2 * h), dtype=torch.float32, device=dev); f[h:h + ny, h:h + nx] = a2d
+        generic.swap_bounds(f, h); return f
+    mk, zh, sh, th = haloed(cdist), haloed(t(z)), haloed(t(sig)), haloed(theta)
+    for wk in modes:
+        plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, nz, h)
+        plan.set_window_kernel(wk)
+        plan.set_static(mk, zh, sh)
+        st = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(4)]
+        for s in range(3):
+            plan.step(cfg.timestep, s + 1, p, u, v, th, *st)
+        plan.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for s in range(6):
+            flush.fill_(float(s)); torch.cuda.synchronize()
+            t0 = time.perf_counter(); plan.step(cfg.timestep, s + 4, p, u, v, th, *st); plan.sync(); ts.append(1e6 * (time.perf_counter() - t0))
+        plan.set_timing(True)
+        ks = []
+        for s in range(4):
+            flush.fill_(float(s)); plan.step(cfg.timestep, s + 10, p, u, v, th, *st); ks.append(plan.last_timing())
+        print(name, "window kernel mode", wk, plan.info()["nn_max"], "step wall us:", " ".join("%.0f" % x for x in ts),
+              "| per-kernel (window, scan, final) us:", " ".join("(%.0f,%.0f,%.0f)" % (a * 1e3, b * 1e3, c * 1e3) for a, b, c in ks))
+        print("   checksum", float(st[3].double().sum()), float(st[2].double().abs().sum()))
+        plan.close()
+else:
+    import ctypes as C
+    from seabreeze_param_b200 import _capi
+    lib = _capi.load(); q = _capi.ptr
+    p = t(synth.pressure_1d(nz))
+    coast = torch.empty((ny, nx), dtype=torch.float32, device=dev); cdist = torch.empty_like(coast); kk = C.c_int(0)
+    _capi.check(lib.sbd_py_get_edges_f32(q(t(land)), q(t(ice)), nx, ny, q(coast)))
+    _capi.check(lib.sbd_py_get_dist_f32(q(coast), q(t(land)), q(t(lon)), q(t(lat)), nx, ny, 180.0, q(cdist), C.byref(kk)))
+    for wk in modes:
+        plan = generic.Plan(SBD_VARIANT_PYTHON, nx, ny, nz)
+        plan.set_window_kernel(wk)
+        plan.set_static(cdist, t(z), t(sig))
+        ws = torch.zeros((ny, nx), dtype=torch.float32, device=dev); wd = torch.zeros_like(ws)
+        out = torch.zeros((4, ny, nx), dtype=torch.float32, device=dev)
+        for s in range(3):
+            plan.step_py(s + 1, cfg.timestep, p, u, v, theta, ws, wd, out)
+        plan.sync()
+        ts = []
+        for s in range(6):
+            flush.fill_(float(s)); torch.cuda.synchronize()
+            t0 = time.perf_counter(); plan.step_py(s + 4, cfg.timestep, p, u, v, theta, ws, wd, out); plan.sync(); ts.append(1e6 * (time.perf_counter() - t0))
+        plan.set_timing(True)
+        ks = []
+        for s in range(4):
+            flush.fill_(float(s)); plan.step_py(s + 10, cfg.timestep, p, u, v, theta, ws, wd, out); ks.append(plan.last_timing()[0])
+        print(name, "window kernel mode", wk, plan.info()["nn_max"], "step wall us:", " ".join("%.0f" % x for x in ts),
+              "| kernel us:", " ".join("%.0f" % (a * 1e3) for a in ks))
+        print("   checksum", float(out[0][out[0] < 1e19].double().sum()), float(out[1].double().sum()))
+        plan.close()

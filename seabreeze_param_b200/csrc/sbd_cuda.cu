@@ -1852,6 +1852,8 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
   }
 }
 
+#include "sbd_win8.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // K4b level scan, scalar form (generic variant; used when nx*ny is not a multiple of 4, p is not
 // 16-byte aligned, or for the UM early-exit scan): one thread per coastal-zone cell of the
@@ -2872,6 +2874,59 @@ int launch_win4(sbd_plan* p, TrigArgs& a)
   return SBD_OK;
 }
 
+// strip form of the window kernel, round 2 (k_win8, sbd_win8.cuh): tile 64 x 32, one float per staged cell
+template <int VARIANT, int NT, bool USE8>
+int launch_win8_cfg(sbd_plan* p, TrigArgs& a)
+{
+  constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
+  constexpr int TX = 64, TY = 32;
+  const int R = a.R;
+  const int WPmax = ((TX + 2 * R + 3) & ~3) + 4;
+  const size_t smem = (size_t)WPmax * (TY + 2 * R) * 4 + TX * TY + (size_t)(TX * TY / 8 + TX * TY / 4 + TX * TY) * 2;
+  auto kern = k_win8<VARIANT, GEN, NT, USE8>;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+  a.nws = p->d_nws;
+  a.nwd = p->d_nwd;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = p->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = (GEN && (a.order == 0 || a.pipe) && !p->timing) ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+  CK(cudaLaunchKernelEx(&cfg, kern, (const TrigArgs)a)); LAUNCHED();
+  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+  if (GEN && a.order == 0) {
+    if (p->timing) CK(cudaEventRecord(p->ev[4], p->stream));
+    if (p->n_coastal > 0) {
+      k_final<<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
+    }
+    if (p->timing) CK(cudaEventRecord(p->ev[5], p->stream));
+  }
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+
+template <int VARIANT>
+int launch_win8(sbd_plan* p, TrigArgs& a)
+{
+  static int cfg_env = -1, min8_env = -1;
+  if (cfg_env < 0) { const char* e = getenv("SBD_WIN8_CFG"); cfg_env = e ? atoi(e) : 1; }
+  if (min8_env < 0) { const char* e = getenv("SBD_WIN8_MIN8"); min8_env = e ? atoi(e) : 0; }
+  a.strip_min = min8_env;
+  // 0: 8-cell strips where the radius allows (measured slower: 32 such strips make a chunk, a tile has only 8
+  //    chunks for its 8 warps and the longest one sets the tile's time); 1 (default): 4-cell strips, 16 chunks;
+  //    2: 4-cell strips, 512 threads
+  if (cfg_env == 0) return launch_win8_cfg<VARIANT, 256, true>(p, a);
+  if (cfg_env == 2) return launch_win8_cfg<VARIANT, 512, false>(p, a);
+  return launch_win8_cfg<VARIANT, 256, false>(p, a);
+}
+
 template <int VARIANT>
 int launch_trigger(sbd_plan* p, TrigArgs& a)
 {
@@ -2879,8 +2934,10 @@ int launch_trigger(sbd_plan* p, TrigArgs& a)
   static int win4_min = -1;
   if (win4_min < 0) { const char* e = getenv("SBD_WIN4_MIN"); win4_min = e ? atoi(e) : 9; }
   const int mode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
-  const bool strips = mode == 2 || (mode == 0 && a.R >= win4_min);
-  if (strips && a.R <= 56) return launch_win4<VARIANT>(p, a);
+  // measured (profiles/r2_probe_win.txt): km-scale radii (c3, halo 54): k_win8 4.1 ms, k_win4 5.1 ms;
+  // 0.1-degree radii (c4, up to 22): k_win4 0.37 ms, k_win8 0.39-0.45 ms
+  if ((mode == 3 || (mode == 0 && a.R >= 32)) && a.R <= 56) return launch_win8<VARIANT>(p, a);
+  if ((mode == 2 || (mode == 0 && a.R >= win4_min)) && a.R <= 56) return launch_win4<VARIANT>(p, a);
   if (a.R <= 16) {
     static int tile = -1;
     if (tile < 0) { const char* e = getenv("SBD_TILE"); tile = e ? atoi(e) : 0; }
@@ -3078,14 +3135,14 @@ int sbd_plan_set_row_window(sbd_plan* p, int row_lo, int row_hi)
 }
 int sbd_set_window_kernel_default(int mode)
 {
-  if (mode < 0 || mode > 2) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 strips");
+  if (mode < 0 || mode > 3) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 4-cell strips, 3 8-cell strips");
   g_window_kernel_default = mode;
   return SBD_OK;
 }
 int sbd_plan_set_window_kernel(sbd_plan* p, int mode)
 {
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
-  if (mode < 0 || mode > 2) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 strips");
+  if (mode < 0 || mode > 3) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 4-cell strips, 3 8-cell strips");
   p->window_kernel = mode;
   return SBD_OK;
 }

@@ -106,7 +106,7 @@ def test_c3_full_size_properties(oracle):
     th, dp, du, dv = haloed(t(theta)), t(p), t(u), t(v)
     res = {}
     stats = None
-    for wk in (1, 2, 2):
+    for wk in (1, 2, 3, 3):
         plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, nz, h)
         plan.set_window_kernel(wk)
         plan.set_static(mk, zh, sh)
@@ -125,6 +125,8 @@ def test_c3_full_size_properties(oracle):
         plan.close()
     for a, b, nm in zip(res[1], res[2], ("windspeed", "winddir", "thc", "sb_con")):
         assert_bits_equal(a, b, "c3 tile vs strip kernel %s" % nm)  # (1)
+    for a, b, nm in zip(res[1], res[3], ("windspeed", "winddir", "thc", "sb_con")):
+        assert_bits_equal(a, b, "c3 tile vs 8-cell strip kernel %s" % nm)
     assert np.isfinite(res[2][3]).all() and (res[2][3] != 0).any()
     # (3a) a 96-row block run as its own plan (halo rows cut from the full planes, the full grid's sigma
     # statistics injected) reproduces the full-grid rows: the result is decomposition-independent

@@ -98,9 +98,9 @@ def test_exact_parallel_stats_adversarial(oracle):
         assert_bits_equal(sm_o, sm_g, "sigmoid: " + nm)
 
 
-@pytest.mark.parametrize("name,wk", [("t_py", 0), ("c5", 0), ("t_py", 2), ("c5", 2)])
+@pytest.mark.parametrize("name,wk", [("t_py", 0), ("c5", 0), ("t_py", 2), ("c5", 2), ("t_py", 3), ("c5", 3)])
 def test_py_diag_time_loop(oracle, name, wk):
-    """wk = 2 forces the strip window kernel (k_win4) on these small-radius grids."""
+    """wk = 2 / 3 force the strip window kernels (k_win4 / k_win8) on these small-radius grids."""
     with window_kernel(wk):
         _py_diag_time_loop(oracle, name)
 
@@ -130,11 +130,12 @@ def _py_diag_time_loop(oracle, name):
     assert trig > 0
 
 
-@pytest.mark.parametrize("wk", [0, 1])
+@pytest.mark.parametrize("wk", [0, 1, 2, 3])
 def test_py_diag_mid_radius(oracle, wk):
     """Python variant on a 0.5-degree grid: get_dist radius k = 9, search radii up to ~10 cells, so
-    the automatic choice (wk = 0) is the strip window kernel with real 4-cell strips; wk = 1 is the
-    tile kernel.  Same bits as the oracle's literal growing-window loops either way."""
+    the automatic choice (wk = 0) is the 8-cell strip kernel k_win8 (whose 4-strip and single-cell paths
+    carry these radii); wk = 1 is the tile kernel, 2 the round-1 strip kernel k_win4, 3 k_win8 forced.
+    Same bits as the oracle's literal growing-window loops in every form."""
     cfg = synth.Config("t_py_mid", 720, 361, 9, 0, "python", 10.0, False, 60.0, "0.5 degree python-variant test")
     land, ice, lon, lat, z, sig = synth.static_fields(cfg)
     coast = oracle.py_get_edges(land, ice)
@@ -281,9 +282,10 @@ def test_generic_edges_dist(oracle, name):
 
 
 @pytest.mark.parametrize("name,level_scan,wk", [("t_gen", 0, 0), ("t_gen", 1, 0), ("c1", 0, 0), ("t_gen", 0, 2),
-                                                 ("t_gen", 1, 2), ("c1", 0, 2)])
+                                                 ("t_gen", 1, 2), ("c1", 0, 2), ("t_gen", 0, 3), ("t_gen", 1, 3),
+                                                 ("c1", 0, 3)])
 def test_generic_seabreeze_diag_steps(oracle, name, level_scan, wk):
-    """wk = 2 forces the strip window kernel (k_win4) on these small-radius grids."""
+    """wk = 2 / 3 force the strip window kernels (k_win4 / k_win8) on these small-radius grids."""
     with window_kernel(wk):
         _generic_seabreeze_diag_steps(oracle, name, level_scan)
 
@@ -516,13 +518,14 @@ def test_generic_device_pointers_torch(oracle):
     plan.close()
 
 
-@pytest.mark.parametrize("wk", [0, 1])
+@pytest.mark.parametrize("wk", [0, 1, 2])
 @pytest.mark.parametrize("nx,ny,h,filt,expect", [(160, 96, 24, 14.0, "big tile"), (320, 240, 54, 40.0, "big tile"),
                                                    (300, 200, 72, 60.0, "global path")])
 def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
     """km-scale regional grids (config 3): the final search radius reaches tens of cells.  wk = 0: the
-    strip kernel (k_win4, radii up to 56 in shared memory, beyond that the global-memory path);
-    wk = 1: the tile kernel (k_trigger, 128x64 tile with patch-raster order)."""
+    8-cell strip kernel (k_win8, radii up to 56 in shared memory, beyond that the global-memory path);
+    wk = 1: the tile kernel (k_trigger, 128x64 tile with patch-raster order); wk = 2: round 1's 4-cell
+    strip kernel (k_win4)."""
     cfg = synth.Config("t_big", nx, ny, 4, h, "generic", filt, True, 1440.0, "wide-window test")
     case = generic_case(cfg, oracle)
     plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
@@ -542,6 +545,40 @@ def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
         plan.step(cfg.timestep, step, p, u, v, theta_h, *sp, flags=fp)
         for a, b, nm in zip(so, sp, ("windspeed", "winddir", "thc", "sb_con")):
             assert_bits_equal(a, b, "%s step %d" % (nm, step))
+        assert np.array_equal(fo, fp)
+    plan.close()
+
+
+@pytest.mark.parametrize("what", ["negative", "nan", "zero"])
+def test_wide_windows_signed_class_fallback(oracle, what):
+    """k_win8 keeps x = +-t0 in shared memory, which needs t0 >= +0; a tile that stages a negative or
+    NaN t0 must fall back to the per-cell global path and still give the oracle's bits (NaNs included).
+    t0 == 0 (both signs) stays on the fast path."""
+    cfg = synth.Config("t_neg", 200, 130, 3, 30, "generic", 18.0, True, 1440.0, "signed-class fallback test")
+    case = generic_case(cfg, oracle)
+    ny, nx, h = cfg.ny, cfg.nx, cfg.h
+    plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, h)
+    plan.set_window_kernel(3)
+    plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
+    assert plan.info()["nn_max"] >= 12, plan.info()
+    so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    sp = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    for step in (1, 2):
+        theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
+        if what == "negative":
+            theta_h[h + 40:h + 44, h + 70:h + 90] = -5.0      # one patch of cells below zero
+            theta_h[h + 100, h + 150] = -300.0
+        elif what == "nan":
+            theta_h[h + 64, h + 100] = np.nan
+        else:
+            theta_h[h + 30:h + 60, h + 20:h + 120] = case["z_h"][h + 30:h + 60, h + 20:h + 120] * 0.0   # t0 = +0 over sea
+            theta_h[h + 61, h + 30] = -0.0
+        fo = oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"], case["sigma_h"],
+                                   *so, cfg.h, literal=False)
+        fp = np.zeros((ny, nx), np.uint8)
+        plan.step(cfg.timestep, step, p, u, v, theta_h, *sp, flags=fp)
+        for a, b, nm in zip(so, sp, ("windspeed", "winddir", "thc", "sb_con")):
+            assert_bits_equal(a, b, "%s %s step %d" % (what, nm, step))
         assert np.array_equal(fo, fp)
     plan.close()
 

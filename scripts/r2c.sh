@@ -1,3 +1,3 @@
 #!/bin/bash
 cd ${GRAFT_REPO_ROOT:-.}; mkdir -p gpurun_out
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_win8 -s 4 -c 1 -o gpurun_out/r2f_win8_c3s python scripts/probe_win.py c3s 3 > gpurun_out/r2f_ncu_c3s.log 2>&1; echo "ncu c3s rc=$?"
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_step_quad -s 6 -c 1 -o gpurun_out/r2j_stepq python bench.py --no-cpu-baseline --no-e2e --steps 6 --warmup 3 > gpurun_out/r2j_ncu.log 2>&1; echo "ncu rc=$?"

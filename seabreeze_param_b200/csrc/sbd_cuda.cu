@@ -2159,6 +2159,8 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
   }
 }
 
+#include "sbd_stepq.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // K4 fused step (generic variant, coarse grids): ONE launch per timestep.  A CTA owns a 64x16-cell
 // tile and splits into two roles that run side by side on the same SM:
@@ -2440,6 +2442,11 @@ struct QuadFlag {
   }
 };
 
+struct QuadOffFlag {
+  QuadFlag f;
+  __host__ __device__ __forceinline__ bool operator()(const int& m) const { return !f(m); }
+};
+
 // flag functor for the compaction of coastal-zone cells (interior, raster order)
 struct ActiveFlag {
   const uint16_t* code;
@@ -2486,6 +2493,8 @@ struct sbd_plan {
   int* d_idx = nullptr;       // compacted raster-ordered list of coastal-zone cells (dense index)
   int* d_quads = nullptr;     // compacted list of aligned quads holding >= 1 coastal-zone cell
   int n_quads = 0;
+  int* d_quads_off = nullptr; // ... and of the quads holding none (k_step_quad fills their sb_con)
+  int n_quads_off = 0;
   void* d_cub = nullptr;      // cub temp storage
   size_t cub_bytes = 0;
   float* d_nws = nullptr;     // scratch: wind speed at the selected level (scan -> window kernel)
@@ -2687,6 +2696,33 @@ int launch_scan_quad(sbd_plan* p, const TrigArgs& a, int qsmem, bool pdl, int q0
   const int* quads = p->d_quads + q0;
   int nq = q1 - q0;
   CK(cudaLaunchKernelEx(&cfg, k_scan_quad<G, QNT>, a, quads, nq));
+  return SBD_OK;
+}
+
+// the whole generic step as one kernel (k_step_quad, sbd_stepq.cuh): quads [q0, q1) of the compacted list,
+// fill = also set sb_con of the quads that hold no coastal-zone cell
+bool stepq_ok(const sbd_plan* p, const TrigArgs& a)
+{
+  auto al = [](const void* q, uintptr_t m) { return (((uintptr_t)q) & m) == 0; };
+  return p->variant == SBD_VARIANT_GENERIC && p->n_quads > 0 && p->nn_max <= 8 && (p->nx % 4) == 0 &&
+         a.prm.level_scan == 0 && al(a.p, 15) && al(a.u, 15) && al(a.v, 15) && al(a.ws, 15) && al(a.wd, 15) &&
+         al(a.thc, 15) && al(a.sb, 15) && al(a.flags, 3);
+}
+int launch_stepq(sbd_plan* p, const TrigArgs& a, int q0, int q1, bool fill)
+{
+  constexpr int NT = 128, B = 5;
+  const int nq = q1 - q0, noff = fill ? p->n_quads_off : 0;
+  const int nb = cdiv(nq, NT) + cdiv(noff, NT);
+  if (p->timing) { CK(cudaEventRecord(p->ev[0], p->stream)); CK(cudaEventRecord(p->ev[1], p->stream)); CK(cudaEventRecord(p->ev[2], p->stream)); }
+  static int minb = -1;   // resident CTAs per SM the kernel is compiled for: 6 (80 registers, default) or 4 (116)
+  if (minb < 0) { const char* e = getenv("SBD_STEPQ_MINB"); minb = e ? atoi(e) : 6; }
+  if (nb > 0) {
+    if (minb == 4) k_step_quad<B, NT, 4><<<nb, NT, 0, p->stream>>>(a, p->d_quads + q0, nq, p->d_quads_off, noff);
+    else k_step_quad<B, NT, 6><<<nb, NT, 0, p->stream>>>(a, p->d_quads + q0, nq, p->d_quads_off, noff);
+    LAUNCHED();
+  }
+  if (p->timing) CK(cudaEventRecord(p->ev[3], p->stream));
+  CK(cudaGetLastError());
   return SBD_OK;
 }
 
@@ -2933,7 +2969,8 @@ int launch_trigger(sbd_plan* p, TrigArgs& a)
   // radii beyond a few cells: strip kernel (see k_win4); sbd_plan_set_window_kernel overrides
   static int win4_min = -1;
   if (win4_min < 0) { const char* e = getenv("SBD_WIN4_MIN"); win4_min = e ? atoi(e) : 9; }
-  const int mode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
+  int mode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
+  if (mode == 4) mode = 0;   // the fused quad step is chosen in sbd_plan_step; here: the window kernel of the other paths
   // measured (profiles/r2_probe_win.txt): km-scale radii (c3, halo 54): k_win8 4.1 ms, k_win4 5.1 ms;
   // 0.1-degree radii (c4, up to 22): k_win4 0.37 ms, k_win8 0.39-0.45 ms
   if ((mode == 3 || (mode == 0 && a.R >= 32)) && a.R <= 56) return launch_win8<VARIANT>(p, a);
@@ -3071,6 +3108,7 @@ int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, 
       cudaMalloc((void**)&p->d_cnt, 4 * sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_idx, (size_t)nx * ny * sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_quads, ((size_t)nx * ny / 4 + 1) * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void**)&p->d_quads_off, ((size_t)nx * ny / 4 + 1) * sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_nws, (size_t)nx * ny * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_nwd, (size_t)nx * ny * sizeof(float)) != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "cudaMalloc of plan planes failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -3086,7 +3124,7 @@ void sbd_plan_destroy(sbd_plan* p)
   if (!p) return;
   if (p->own_stream) cudaStreamSynchronize(p->own_stream);
   cudaFree(p->d_gzsm); cudaFree(p->d_code); cudaFree(p->d_cl); cudaFree(p->d_stats); cudaFree(p->d_carry); cudaFree(p->d_cnt);
-  cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads); cudaFree(p->d_nws); cudaFree(p->d_nwd);
+  cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads); cudaFree(p->d_quads_off); cudaFree(p->d_nws); cudaFree(p->d_nwd);
   for (int i = 0; i < 6; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->e_copy) cudaEventDestroy(p->e_copy);
@@ -3135,14 +3173,14 @@ int sbd_plan_set_row_window(sbd_plan* p, int row_lo, int row_hi)
 }
 int sbd_set_window_kernel_default(int mode)
 {
-  if (mode < 0 || mode > 3) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 4-cell strips, 3 8-cell strips");
+  if (mode < 0 || mode > 4) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 k_win4, 3 k_win8, 4 fused quad step");
   g_window_kernel_default = mode;
   return SBD_OK;
 }
 int sbd_plan_set_window_kernel(sbd_plan* p, int mode)
 {
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
-  if (mode < 0 || mode > 3) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 4-cell strips, 3 8-cell strips");
+  if (mode < 0 || mode > 4) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 k_win4, 3 k_win8, 4 fused quad step");
   p->window_kernel = mode;
   return SBD_OK;
 }
@@ -3173,7 +3211,7 @@ int sbd_plan_last_timing(sbd_plan* p, float* ms3)
   ms3[0] = ms3[1] = ms3[2] = 0.0f;
   CK(cudaStreamSynchronize(p->stream));
   CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));              // window kernel (or the fused step kernel)
-  if (p->variant == SBD_VARIANT_GENERIC && p->last_order != 2) {
+  if (p->variant == SBD_VARIANT_GENERIC && p->last_order != 2) {   // (last_order 3: the one-kernel step sits in the scan slot)
     CK(cudaEventElapsedTime(&ms3[1], p->ev[2], p->ev[3]));            // level-scan kernel
     if (p->last_order == 0) CK(cudaEventElapsedTime(&ms3[2], p->ev[4], p->ev[5]));  // threshold kernel
   }
@@ -3268,6 +3306,25 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
       }
       CK(cub::DeviceSelect::If(p->d_cub, need2, it, p->d_quads, p->d_cnt + 3, n2 / 4, qf, st));
       LAUNCHED();
+      // the complement: quads without any coastal-zone cell (static; filled with the missing value every step)
+      QuadOffFlag qo{qf};
+      size_t need3 = 0;
+      CK(cub::DeviceSelect::If(nullptr, need3, it, p->d_quads_off, p->d_cnt + 2, n2 / 4, qo, st));
+      if (need3 > p->cub_bytes) {
+        CK(cudaStreamSynchronize(st));
+        CK(cudaFree(p->d_cub));
+        p->d_cub = nullptr;
+        CK(cudaMalloc(&p->d_cub, need3));
+        p->cub_bytes = need3;
+      }
+      int n_act = 0;
+      CK(cudaMemcpyAsync(&n_act, p->d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));   // keep the cell count
+      CK(cudaStreamSynchronize(st));
+      CK(cub::DeviceSelect::If(p->d_cub, need3, it, p->d_quads_off, p->d_cnt + 2, n2 / 4, qo, st));
+      LAUNCHED();
+      CK(cudaMemcpyAsync(&p->n_quads_off, p->d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpyAsync(p->d_cnt + 2, &n_act, sizeof(int), cudaMemcpyHostToDevice, st));
     }
   }
   int cnt[4];
@@ -3464,6 +3521,38 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
     a.order = 0; p->last_order = 0;
     if ((rc = launch_scan(p, a))) return rc;
     if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
+    return flush_out(p, pend, any_host);
+  }
+  // Small search radii (N512-class grids): the whole step is ONE kernel -- every level-scan thread also sums
+  // the windows of its four cells (sbd_stepq.cuh).  sbd_plan_set_window_kernel(1..3) keeps the two-kernel forms.
+  const int wmode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
+  const bool p_map = !is_device_ptr(pp) && a.p != nullptr && mapped_host_ptr(pp) == a.p;
+  if ((wmode == 0 || wmode == 4) && stepq_ok(p, a) && !p->pipelined) {
+    a.order = 1; p->last_order = 3;
+    if (p_map && p->n_quads_top > 0 && !p->timing) {
+      // hybrid transfer for pinned host p (see below): southern quads gather in place, northern rows by DMA
+      if (!p->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&p->e_copy, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->e_main, cudaEventDisableTiming));
+        CK(cudaMalloc((void**)&p->d_pfull, n3 * sizeof(float)));
+      }
+      CK(cudaEventRecord(p->e_main, p->stream));
+      CK(cudaStreamWaitEvent(p->copy_stream, p->e_main, 0));
+      CK(cudaMemcpy2DAsync(p->d_pfull + (size_t)p->yfirst * p->nx, n2 * sizeof(float),
+                           pp + (size_t)p->yfirst * p->nx, n2 * sizeof(float),
+                           (size_t)(p->ysplit - p->yfirst) * p->nx * sizeof(float), p->nz, cudaMemcpyHostToDevice,
+                           p->copy_stream));
+      CK(cudaEventRecord(p->e_copy, p->copy_stream));
+      if ((rc = launch_stepq(p, a, p->n_quads_top, p->n_quads, true))) return rc;
+      CK(cudaStreamWaitEvent(p->stream, p->e_copy, 0));
+      TrigArgs b = a;
+      b.p = p->d_pfull;
+      b.sync_local = nullptr;   // the handshake ran in the first launch
+      if ((rc = launch_stepq(p, b, 0, p->n_quads_top, false))) return rc;
+      return flush_out(p, pend, any_host);
+    }
+    if ((rc = launch_stepq(p, a, 0, p->n_quads, true))) return rc;
     return flush_out(p, pend, any_host);
   }
   a.order = 1; p->last_order = 1;

@@ -283,9 +283,12 @@ def test_generic_edges_dist(oracle, name):
 
 @pytest.mark.parametrize("name,level_scan,wk", [("t_gen", 0, 0), ("t_gen", 1, 0), ("c1", 0, 0), ("t_gen", 0, 2),
                                                  ("t_gen", 1, 2), ("c1", 0, 2), ("t_gen", 0, 3), ("t_gen", 1, 3),
-                                                 ("c1", 0, 3)])
+                                                 ("c1", 0, 3), ("t_gen", 0, 1), ("c1", 0, 1), ("t_gen", 0, 4),
+                                                 ("c1", 0, 4)])
 def test_generic_seabreeze_diag_steps(oracle, name, level_scan, wk):
-    """wk = 2 / 3 force the strip window kernels (k_win4 / k_win8) on these small-radius grids."""
+    """wk = 0 / 4: the one-kernel step (k_step_quad) where it applies (minloc level search, radii <= 8), wk = 1 the
+    tile window kernel (k_trigger) + level scan, wk = 2 / 3 the strip window kernels (k_win4 / k_win8) forced on
+    these small-radius grids."""
     with window_kernel(wk):
         _generic_seabreeze_diag_steps(oracle, name, level_scan)
 

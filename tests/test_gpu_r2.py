@@ -155,3 +155,29 @@ def test_reference_python_wrapper_runs_on_the_dropin(oracle, tmp_path):
     assert_bits_equal(ws, got["ws"].astype(np.float32), "windspeed")
     assert_bits_equal(wd, got["wd"].astype(np.float32), "winddir")
     assert_bits_equal(last_t0, got["thc"].astype(np.float32), "thc (= t0, I:244)")
+
+
+@pytest.mark.parametrize("name", ["ref_py_a.npz", "ref_py_b.npz"])
+def test_cuda_path_reproduces_reference_source_goldens(name):
+    """tests/golden/ref_*.npz were produced by the reference's own .f90 files (executed by tests/golden/f90interp.py,
+    see make_reference_golden.py): the CUDA path, through the f2py-compatible module, must give the same bits --
+    get_edges, get_dist and the diag() records with the state threaded as the reference wrapper does."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", name))
+    land, z, sig, lon, lat, p = (d[k] for k in ("land", "z", "sig", "lon", "lat", "p"))
+    kw = {k[3:]: float(d[k]) for k in d.files if k.startswith("kw_")}
+    ws = np.zeros_like(z); wd = np.zeros_like(z); thc = np.zeros_like(z)
+    for r in range(d["theta"].shape[0]):
+        coast = seabreeze.get_edges(F(land), F(d["ci"][r]))
+        assert_bits_equal(F(d["coast"][r]), coast, "%s get_edges record %d" % (name, r))
+        cd = seabreeze.get_dist(coast, F(land), lon, lat, maxdist=float(d["dist_maxdist"]))
+        assert_bits_equal(F(d["cdist"][r]), cd, "%s get_dist record %d" % (name, r))
+        out = seabreeze.diag(1 + r, p, F(z), F(sig), F(d["theta"][r]), F(d["v"][r]), F(d["u"][r]), cd, F(ws), F(wd),
+                             F(thc), **kw)
+        got = seabreezediag.c2f(out)
+        ref = d["out"][r]
+        for k, nm in enumerate(("sb_con", "t0", "windspeed", "winddir")):
+            w = ~np.isnan(ref[k])     # NaN: never written by the reference (last row, P:165)
+            assert_bits_equal(np.where(w, ref[k], 0).astype(np.float32), np.where(w, got[k], 0).astype(np.float32),
+                              "%s %s record %d" % (name, nm, r))
+        thc, ws, wd = [np.where(np.isnan(ref[k]), prev, ref[k]).astype(np.float32)
+                       for k, prev in ((1, thc), (2, ws), (3, wd))]

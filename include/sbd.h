@@ -28,6 +28,7 @@
 #ifndef SBD_H
 #define SBD_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -100,6 +101,21 @@ int sbd_seabreeze_diag_f32(float timestep, int timestep_number, const float* p, 
                            const float* sigma, float* windspeed, float* winddir, float* thc,
                            float* sb_con, int nx, int ny, int nz, int h, const sbd_params* prm,
                            uint8_t* flags);
+
+/* The one-shot entry points above (and sbd_py_diag_f32 below) keep a small process-wide cache of plans keyed by
+ * variant, dimensions and tunables, so that the call a host model makes every timestep
+ * (generic/dummy_model.f90:52-54) does not redo the static work: the three static planes are uploaded (or read
+ * in place when they are device pointers), checksummed on the device, and the sigmoid statistics / search radii /
+ * work lists are rebuilt only when their content changed.  sbd_plan_cache_clear frees the cached plans. */
+int sbd_plan_cache_clear(void);
+int sbd_plan_cache_stats(int* hits, int* misses, int* plans);
+
+/* Page-lock and device-map a caller's host array (cudaHostRegister): later calls that receive it move data at
+ * PCIe rate, and p, u, v are gathered in place by the level scan (only the columns of coastal-zone cells cross the
+ * bus).  The range must stay allocated until sbd_host_unregister.  A Fortran host registers its model arrays once
+ * at start-up; seabreeze_param_b200 registers numpy arrays with a finalizer (SBD_AUTO_REGISTER=0 disables). */
+int sbd_host_register(const void* ptr, size_t bytes);
+int sbd_host_unregister(const void* ptr);
 
 /* swap_bounds(field, halo_size)  H:12-17 (stub) / U:408-410.  Single-domain halo fill:
  * east-west periodic, north-south edge-replicated.  The multi-GPU halo swap (NCCL send/recv between

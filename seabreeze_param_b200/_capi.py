@@ -24,6 +24,7 @@ SYMBOLS = [
     "sbd_launch_count", "sbd_stats_chain_f32", "sbd_plan_set_timing", "sbd_plan_last_timing", "sbd_plan_set_halo_mode", "sbd_plan_set_peer_theta",
     "sbd_plan_set_peer_sync", "sbd_plan_set_pipelined", "sbd_plan_set_window_kernel", "sbd_set_window_kernel_default", "sbd_plan_set_row_window", "sbd_get_edges_ex_f32", "sbd_plan_window_info",
     "sbd_get_edges_f64", "sbd_get_dist_f64", "sbd_sigmoid_f64", "sbd_seabreeze_diag_f64", "sbd_swap_bounds_f64",
+    "sbd_plan_cache_clear", "sbd_plan_cache_stats", "sbd_host_register", "sbd_host_unregister",
 ]
 
 
@@ -114,6 +115,9 @@ def load():
     lib.sbd_plan_set_timing.argtypes = [vp, i]
     lib.sbd_plan_last_timing.argtypes = [vp, fp]
     lib.sbd_stats_chain_f32.argtypes = [fp, i, i, i, i, i, fp]
+    lib.sbd_plan_cache_stats.argtypes = [ip, ip, ip]
+    lib.sbd_host_register.argtypes = [vp, C.c_size_t]
+    lib.sbd_host_unregister.argtypes = [vp]
     _LIB = lib
     return lib
 
@@ -135,6 +139,38 @@ def ptr(a):
     if hasattr(a, "data_ptr"):
         return a.data_ptr()
     raise TypeError("cannot take the address of %r" % type(a))
+
+
+_REGISTERED = {}   # address -> (bytes, finalizer)
+
+
+def auto_register(a, min_bytes=1 << 20):
+    """Page-lock + device-map a large host numpy array the first time the library sees it, and undo that when the
+    array (or the buffer it views) is garbage collected.  No-op for small / non-numpy / non-owning-unknown arrays,
+    when there is no device, or with SBD_AUTO_REGISTER=0."""
+    import weakref
+    if not isinstance(a, np.ndarray) or a.nbytes < min_bytes or os.environ.get("SBD_AUTO_REGISTER", "1") == "0":
+        return
+    addr = a.ctypes.data
+    ent = _REGISTERED.get(addr)
+    if ent is not None and ent[0] >= a.nbytes:
+        return
+    owner = a
+    while isinstance(owner.base, np.ndarray):
+        owner = owner.base
+    if owner.base is not None:      # memory owned by a foreign object (torch pinned tensor, mmap, ...): leave it alone
+        return
+    lib = load()
+    if lib.sbd_device_count() < 1 or lib.sbd_host_register(addr, a.nbytes) != 0:
+        return
+
+    def _drop(addr=addr):
+        _REGISTERED.pop(addr, None)
+        try:
+            lib.sbd_host_unregister(addr)
+        except Exception:
+            pass
+    _REGISTERED[addr] = (a.nbytes, weakref.finalize(owner, _drop))
 
 
 def default_params(variant):

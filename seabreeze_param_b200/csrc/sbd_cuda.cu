@@ -1853,6 +1853,7 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
 }
 
 #include "sbd_win8.cuh"
+#include "sbd_wsmall.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K4b level scan, scalar form (generic variant; used when nx*ny is not a multiple of 4, p is not
@@ -2458,6 +2459,31 @@ struct ActiveFlag {
   }
 };
 
+// content checksum of the static planes (one-shot entry points: plan cache): two 64-bit sums
+// per plane -- of the bit patterns, and of the bit patterns weighted by an odd function of the position
+__global__ void __launch_bounds__(256) k_checksum3(const float* __restrict__ a0, const float* __restrict__ a1,
+                                                   const float* __restrict__ a2, long long n,
+                                                   unsigned long long* __restrict__ sums)
+{
+  unsigned long long s[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+  const float* arr[3] = {a0, a1, a2};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long w = 2ull * (unsigned long long)i + 1ull;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned long long b = __float_as_uint(arr[k][i]);
+      s[2 * k] += b;
+      s[2 * k + 1] += b * w * 0x9E3779B97F4A7C15ull;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    unsigned long long v = s[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sums + k, v);
+  }
+}
+
 // 64-bit <-> 32-bit REAL conversion for the _f64 twins of the C-ABI (round to nearest / exact widening)
 __global__ void k_narrow(const double* __restrict__ src, float* __restrict__ dst, long long n)
 {
@@ -2493,6 +2519,11 @@ struct sbd_plan {
   int* d_idx = nullptr;       // compacted raster-ordered list of coastal-zone cells (dense index)
   int* d_quads = nullptr;     // compacted list of aligned quads holding >= 1 coastal-zone cell
   int n_quads = 0;
+  // one-shot entry points (plan cache): device copies of the caller's static planes + their content checksum
+  float* d_st_in[3] = {nullptr, nullptr, nullptr};
+  unsigned long long* d_sum = nullptr;
+  unsigned long long static_sum[6] = {0, 0, 0, 0, 0, 0};
+  bool sum_valid = false;
   int* d_quads_off = nullptr; // ... and of the quads holding none (k_step_quad fills their sb_con)
   int n_quads_off = 0;
   void* d_cub = nullptr;      // cub temp storage
@@ -2963,6 +2994,42 @@ int launch_win8(sbd_plan* p, TrigArgs& a)
   return launch_win8_cfg<VARIANT, 256, false>(p, a);
 }
 
+// small-radius window kernel (k_wsmall, sbd_wsmall.cuh): 32 x 8 cells per CTA, one thread per cell
+template <int VARIANT>
+int launch_wsmall(sbd_plan* p, TrigArgs& a)
+{
+  constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
+  constexpr int TX = 32, TY = 8, NT = 256;
+  const int R = a.R;
+  const size_t smem = (size_t)((TX + 2 * R) | 1) * (TY + 2 * R) * 4;
+  auto kern = k_wsmall<VARIANT, GEN>;
+  dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+  a.nws = p->d_nws;
+  a.nwd = p->d_nwd;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = p->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = (GEN && (a.order == 0 || a.pipe) && !p->timing) ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+  CK(cudaLaunchKernelEx(&cfg, kern, (const TrigArgs)a)); LAUNCHED();
+  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
+  if (GEN && a.order == 0) {
+    if (p->timing) CK(cudaEventRecord(p->ev[4], p->stream));
+    if (p->n_coastal > 0) {
+      k_final<<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
+    }
+    if (p->timing) CK(cudaEventRecord(p->ev[5], p->stream));
+  }
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+
 template <int VARIANT>
 int launch_trigger(sbd_plan* p, TrigArgs& a)
 {
@@ -2973,6 +3040,7 @@ int launch_trigger(sbd_plan* p, TrigArgs& a)
   if (mode == 4) mode = 0;   // the fused quad step is chosen in sbd_plan_step; here: the window kernel of the other paths
   // measured (profiles/r2_probe_win.txt): km-scale radii (c3, halo 54): k_win8 4.1 ms, k_win4 5.1 ms;
   // 0.1-degree radii (c4, up to 22): k_win4 0.37 ms, k_win8 0.39-0.45 ms
+  if ((mode == 5 || mode == 0) && a.R <= 8) return launch_wsmall<VARIANT>(p, a);
   if ((mode == 3 || (mode == 0 && a.R >= 32)) && a.R <= 56) return launch_win8<VARIANT>(p, a);
   if ((mode == 2 || (mode == 0 && a.R >= win4_min)) && a.R <= 56) return launch_win4<VARIANT>(p, a);
   if (a.R <= 16) {
@@ -3130,6 +3198,8 @@ void sbd_plan_destroy(sbd_plan* p)
   if (p->e_copy) cudaEventDestroy(p->e_copy);
   if (p->e_main) cudaEventDestroy(p->e_main);
   cudaFree(p->d_pfull); cudaFree(p->d_thc_scr[0]);
+  for (int i = 0; i < 3; ++i) cudaFree(p->d_st_in[i]);
+  cudaFree(p->d_sum);
   for (auto& s : p->stage) cudaFree(s.first);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   delete p;
@@ -3173,14 +3243,14 @@ int sbd_plan_set_row_window(sbd_plan* p, int row_lo, int row_hi)
 }
 int sbd_set_window_kernel_default(int mode)
 {
-  if (mode < 0 || mode > 4) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 k_win4, 3 k_win8, 4 fused quad step");
+  if (mode < 0 || mode > 5) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 k_win4, 3 k_win8, 4 fused quad step, 5 k_wsmall");
   g_window_kernel_default = mode;
   return SBD_OK;
 }
 int sbd_plan_set_window_kernel(sbd_plan* p, int mode)
 {
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
-  if (mode < 0 || mode > 4) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 k_win4, 3 k_win8, 4 fused quad step");
+  if (mode < 0 || mode > 5) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 k_win4, 3 k_win8, 4 fused quad step, 5 k_wsmall");
   p->window_kernel = mode;
   return SBD_OK;
 }
@@ -3527,7 +3597,7 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
   // the windows of its four cells (sbd_stepq.cuh).  sbd_plan_set_window_kernel(1..3) keeps the two-kernel forms.
   const int wmode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
   const bool p_map = !is_device_ptr(pp) && a.p != nullptr && mapped_host_ptr(pp) == a.p;
-  if ((wmode == 0 || wmode == 4) && stepq_ok(p, a) && !p->pipelined) {
+  if (wmode == 4 && stepq_ok(p, a) && !p->pipelined) {   // measured slower than the two-kernel step: opt-in only
     a.order = 1; p->last_order = 3;
     if (p_map && p->n_quads_top > 0 && !p->timing) {
       // hybrid transfer for pinned host p (see below): southern quads gather in place, northern rows by DMA
@@ -3654,18 +3724,139 @@ int sbd_plan_step_py(sbd_plan* p, int step, float timestep_min, const float* pp,
 // ---------------------------------------------------------------------------------------------
 // one-shot entry points
 // ---------------------------------------------------------------------------------------------
+// The reference's own calls -- seabreeze_diag(...) from a host model every timestep (generic/dummy_model.f90:52-54),
+// diag(...) from the python wrapper every record -- hand over the static fields every time.  Behind them sits a
+// small process-wide cache of plans keyed by variant, dimensions and tunables; a call uploads the three static
+// planes (or reads them in place when they are device pointers), checksums them on the device and rebuilds the
+// derived planes (sigmoid statistics, search radii, work lists: 2-50 ms) only when the content changed.
+namespace {
+struct CachedPlan { sbd_plan* p; unsigned long long stamp; };
+std::mutex g_cache_mu;
+std::vector<CachedPlan> g_cache;
+unsigned long long g_cache_clock = 0;
+int g_cache_hits = 0, g_cache_misses = 0;
+constexpr size_t kCacheMax = 4;
+
+sbd_plan* cache_find_or_create(int variant, int nx, int ny, int nz, int h, const sbd_params& q, int* rc)
+{
+  for (auto& e : g_cache) {
+    sbd_plan* p = e.p;
+    if (p->variant == variant && p->nx == nx && p->ny == ny && p->nz == nz &&
+        p->h == (variant == SBD_VARIANT_GENERIC ? h : 0) && memcmp(&p->prm, &q, sizeof q) == 0 &&
+        p->window_kernel == 0) {
+      e.stamp = ++g_cache_clock;
+      return p;
+    }
+  }
+  sbd_plan* p = nullptr;
+  *rc = sbd_plan_create(&p, variant, nx, ny, nz, h, &q);
+  if (*rc) return nullptr;
+  if (g_cache.size() >= kCacheMax) {
+    size_t lru = 0;
+    for (size_t i = 1; i < g_cache.size(); ++i) if (g_cache[i].stamp < g_cache[lru].stamp) lru = i;
+    sbd_plan_destroy(g_cache[lru].p);
+    g_cache.erase(g_cache.begin() + lru);
+  }
+  g_cache.push_back({p, ++g_cache_clock});
+  return p;
+}
+
+// set_static with a content check: returns with the plan's derived planes valid for (mask, z, sigma)
+int set_static_cached(sbd_plan* p, const float* mask, const float* z, const float* sigma)
+{
+  if (!mask || !z || !sigma) return fail(SBD_EINVAL, "NULL argument");
+  const size_t n = plane_elems(p);
+  const float* src[3] = {mask, z, sigma};
+  const float* dev[3];
+  cudaStream_t st = p->stream;
+  if (!p->d_sum) CK(cudaMalloc((void**)&p->d_sum, 6 * sizeof(unsigned long long)));
+  for (int i = 0; i < 3; ++i) {
+    if (is_device_ptr(src[i])) { dev[i] = src[i]; continue; }
+    if (!p->d_st_in[i]) CK(cudaMalloc((void**)&p->d_st_in[i], n * sizeof(float)));
+    CK(cudaMemcpyAsync(p->d_st_in[i], src[i], n * sizeof(float), cudaMemcpyHostToDevice, st));
+    dev[i] = p->d_st_in[i];
+  }
+  CK(cudaMemsetAsync(p->d_sum, 0, 6 * sizeof(unsigned long long), st));
+  k_checksum3<<<296, 256, 0, st>>>(dev[0], dev[1], dev[2], (long long)n, p->d_sum); LAUNCHED();
+  unsigned long long sum[6];
+  CK(cudaMemcpyAsync(sum, p->d_sum, sizeof sum, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (p->have_static && p->sum_valid && memcmp(sum, p->static_sum, sizeof sum) == 0) { ++g_cache_hits; return SBD_OK; }
+  ++g_cache_misses;
+  p->have_static = false;
+  int rc;
+  if ((rc = plan_build_gzsm(p, dev[1], dev[2], nullptr))) return rc;
+  if ((rc = plan_build_code(p, dev[0]))) return rc;
+  CK(cudaMemcpyAsync(p->stats, p->d_stats, sizeof p->stats, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(p->static_sum, sum, sizeof sum);
+  p->sum_valid = true;
+  p->have_static = true;
+  return SBD_OK;
+}
+}  // namespace
+
+int sbd_plan_cache_clear(void)
+{
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& e : g_cache) sbd_plan_destroy(e.p);
+  g_cache.clear();
+  return SBD_OK;
+}
+int sbd_plan_cache_stats(int* hits, int* misses, int* plans)
+{
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (hits) *hits = g_cache_hits;
+  if (misses) *misses = g_cache_misses;
+  if (plans) *plans = (int)g_cache.size();
+  return SBD_OK;
+}
+
+// Page-lock and device-map a caller's host array once, so that every later call that receives it moves data at
+// PCIe rate and -- for p, u, v -- lets the level scan gather only the columns it needs in place (zero copy).
+// The range must stay allocated until sbd_host_unregister: a registration that outlives its allocation would keep
+// reading the old pages.  Fortran hosts register their (static) model arrays at start-up; the Python layer
+// registers numpy arrays with a finalizer that unregisters them when the array is collected.
+int sbd_host_register(const void* ptr, size_t bytes)
+{
+  if (!ptr || !bytes) return fail(SBD_EINVAL, "NULL / empty range");
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return SBD_OK;  // already pinned / device
+  cudaGetLastError();
+  cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return SBD_OK; }
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof g_err, "cudaHostRegister(%p, %zu) -> %s", ptr, bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return SBD_ECUDA;
+  }
+  return SBD_OK;
+}
+int sbd_host_unregister(const void* ptr)
+{
+  if (!ptr) return fail(SBD_EINVAL, "NULL");
+  cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(SBD_EINVAL, "range was not registered"); }
+  return SBD_OK;
+}
+
 int sbd_seabreeze_diag_f32(float timestep, int step, const float* pp, const float* u, const float* v,
                            const float* theta, const float* mask, const float* z, const float* sigma,
                            float* ws, float* wd, float* thc, float* sb, int nx, int ny, int nz, int h,
                            const sbd_params* prm, uint8_t* flags)
 {
-  sbd_plan* p = nullptr;
-  int rc = sbd_plan_create(&p, SBD_VARIANT_GENERIC, nx, ny, nz, h, prm);
-  if (rc) return rc;
-  rc = sbd_plan_set_static(p, mask, z, sigma, nullptr);
+  if (nx < 1 || ny < 1 || nz < 1) return fail(SBD_EDIMS, "nx, ny, nz must be >= 1");  // U:198-201
+  sbd_params q;
+  if (prm) q = *prm; else sbd_default_params(&q, SBD_VARIANT_GENERIC);
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  int rc = SBD_OK;
+  sbd_plan* p = cache_find_or_create(SBD_VARIANT_GENERIC, nx, ny, nz, h, q, &rc);
+  if (!p) return rc;
+  rc = set_static_cached(p, mask, z, sigma);
   if (!rc) rc = sbd_plan_step(p, timestep, step, pp, u, v, theta, ws, wd, thc, sb, flags);
   if (!rc) rc = sbd_plan_sync(p);
-  sbd_plan_destroy(p);
   return rc;
 }
 
@@ -3682,13 +3873,14 @@ int sbd_py_diag_f32(int step, const float* pp, const float* z, const float* stdo
   q.target_time = target_time * (60.0f * 60.0f);  // P:147
   q.thresh_wind = thresh_wind; q.thresh_winddir = thresh_winddir; q.thresh_windch = thresh_windch;
   q.thresh_thc = thresh_thc; q.maxdist = maxdist;
-  sbd_plan* p = nullptr;
-  int rc = sbd_plan_create(&p, SBD_VARIANT_PYTHON, nlons, nlats, nps, 0, &q);
-  if (rc) return rc;
-  rc = sbd_plan_set_static(p, cdist, z, stdo, nullptr);
+  if (nlons < 1 || nlats < 1 || nps < 1) return fail(SBD_EDIMS, "nlons, nlats, nps must be >= 1");
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  int rc = SBD_OK;
+  sbd_plan* p = cache_find_or_create(SBD_VARIANT_PYTHON, nlons, nlats, nps, 0, q, &rc);
+  if (!p) return rc;
+  rc = set_static_cached(p, cdist, z, stdo);
   if (!rc) rc = sbd_plan_step_py(p, step, timestep, pp, u, v, theta, ws, wd, output, flags);
   if (!rc) rc = sbd_plan_sync(p);
-  sbd_plan_destroy(p);
   return rc;
 }
 

@@ -87,7 +87,8 @@ def seabreeze_diag(timestep, timestep_number, p, u, v, theta, mask, z, sigma, wi
                    sb_con, params=None, flags=None):
     """call seabreeze_diag(timestep, timestep_number, p, u, v, theta, mask, z, sigma, windspeed,
     winddir, thc, sb_con)  (G:55-271, dummy-argument names of G:55-56; pass by keyword to be
-    order-agnostic).  One-shot: static fields are processed on every call."""
+    order-agnostic).  The library keeps the plan of the last few (dimensions, tunables) and redoes the
+    static work only when mask, z or sigma changed (content checksum)."""
     nz, ny, nx = p.shape
     h = (theta.shape[1] - nx) // 2
     for name, a in (("u", u), ("v", v)):
@@ -99,6 +100,8 @@ def seabreeze_diag(timestep, timestep_number, p, u, v, theta, mask, z, sigma, wi
     lib = _capi.load()
     q = _capi.ptr
     prm = C.byref(params) if params is not None else None
+    for a in (p, u, v, theta, mask, z, sigma, windspeed, winddir, thc, sb_con):
+        _capi.auto_register(a)   # large host arrays: page-locked once, then PCIe rate / zero-copy gather
     _capi.check(lib.sbd_seabreeze_diag_f32(float(timestep), int(timestep_number), q(p), q(u), q(v), q(theta),
                                            q(mask), q(z), q(sigma), q(windspeed), q(winddir), q(thc),
                                            q(sb_con), nx, ny, nz, h, prm, q(flags)), "seabreeze_diag")

@@ -98,9 +98,11 @@ def test_exact_parallel_stats_adversarial(oracle):
         assert_bits_equal(sm_o, sm_g, "sigmoid: " + nm)
 
 
-@pytest.mark.parametrize("name,wk", [("t_py", 0), ("c5", 0), ("t_py", 2), ("c5", 2), ("t_py", 3), ("c5", 3)])
+@pytest.mark.parametrize("name,wk", [("t_py", 0), ("c5", 0), ("t_py", 2), ("c5", 2), ("t_py", 3), ("c5", 3),
+                                     ("t_py", 1), ("c5", 1)])
 def test_py_diag_time_loop(oracle, name, wk):
-    """wk = 2 / 3 force the strip window kernels (k_win4 / k_win8) on these small-radius grids."""
+    """wk = 0: automatic = the small-radius kernel k_wsmall on these grids; 1: the tile kernel k_trigger;
+    2 / 3 force the strip window kernels (k_win4 / k_win8)."""
     with window_kernel(wk):
         _py_diag_time_loop(oracle, name)
 
@@ -286,9 +288,9 @@ def test_generic_edges_dist(oracle, name):
                                                  ("c1", 0, 3), ("t_gen", 0, 1), ("c1", 0, 1), ("t_gen", 0, 4),
                                                  ("c1", 0, 4)])
 def test_generic_seabreeze_diag_steps(oracle, name, level_scan, wk):
-    """wk = 0 / 4: the one-kernel step (k_step_quad) where it applies (minloc level search, radii <= 8), wk = 1 the
-    tile window kernel (k_trigger) + level scan, wk = 2 / 3 the strip window kernels (k_win4 / k_win8) forced on
-    these small-radius grids."""
+    """wk = 0: automatic = k_wsmall + level scan on these small-radius grids; 1: the tile window kernel (k_trigger);
+    2 / 3: the strip window kernels (k_win4 / k_win8) forced; 4: the one-kernel step (k_step_quad; opt-in, it
+    applies to the minloc level search only)."""
     with window_kernel(wk):
         _generic_seabreeze_diag_steps(oracle, name, level_scan)
 

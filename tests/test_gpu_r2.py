@@ -181,3 +181,46 @@ def test_cuda_path_reproduces_reference_source_goldens(name):
                               "%s %s record %d" % (name, nm, r))
         thc, ws, wd = [np.where(np.isnan(ref[k]), prev, ref[k]).astype(np.float32)
                        for k, prev in ((1, thc), (2, ws), (3, wd))]
+
+
+def test_one_shot_plan_cache_and_host_registration(oracle):
+    """sbd_seabreeze_diag_f32 -- the call dummy_model.f90:52-54 makes every timestep -- keeps its plan between
+    calls: same static fields -> cache hit (no rebuild), changed static field -> rebuild, and the results are the
+    oracle's in both cases.  Large host arrays handed to generic.seabreeze_diag get page-locked (auto_register)."""
+    import ctypes as C
+    from seabreeze_param_b200 import _capi
+    from util import generic_case, generic_step_inputs
+    lib = _capi.load()
+    lib.sbd_plan_cache_clear()
+    cfg = synth.Config("t_cache", 512, 384, 24, 5, "generic", 6.0, False, 1440.0, "plan cache test")
+    case = generic_case(cfg, oracle)
+    ny, nx = cfg.ny, cfg.nx
+    so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    sg = [np.zeros((ny, nx), np.float32) for _ in range(4)]
+    h0, m0, n0 = C.c_int(), C.c_int(), C.c_int()
+    lib.sbd_plan_cache_stats(C.byref(h0), C.byref(m0), C.byref(n0))
+
+    def step(k, mask_h):
+        th, p, u, v = generic_step_inputs(cfg, case, k, oracle)
+        fo = oracle.seabreeze_diag(cfg.timestep, k, p, u, v, th, mask_h, case["z_h"], case["sigma_h"], *so, cfg.h)
+        fg = np.zeros((ny, nx), np.uint8)
+        generic.seabreeze_diag(cfg.timestep, k, p, u, v, th, mask_h, case["z_h"], case["sigma_h"], *sg, flags=fg)
+        for a, b, nm in zip(so, sg, ("windspeed", "winddir", "thc", "sb_con")):
+            assert_bits_equal(a, b, "%s step %d" % (nm, k))
+        assert np.array_equal(fo, fg)
+        return p
+
+    p = step(1, case["mask_h"])
+    step(2, case["mask_h"])
+    step(3, case["mask_h"])
+    h1, m1, n1 = C.c_int(), C.c_int(), C.c_int()
+    lib.sbd_plan_cache_stats(C.byref(h1), C.byref(m1), C.byref(n1))
+    assert m1.value - m0.value == 1 and h1.value - h0.value == 2 and n1.value >= 1
+    # a changed static field must be noticed: move the coast (sign flip of one patch of the signed distance)
+    mask2 = case["mask_h"].copy()
+    mask2[100:140, 200:260] *= -1.0
+    step(4, mask2)
+    lib.sbd_plan_cache_stats(C.byref(h1), C.byref(m1), C.byref(n1))
+    assert m1.value - m0.value == 2
+    assert p.nbytes >= (1 << 20) and p.ctypes.data in _capi._REGISTERED    # 18.9 MB p was page-locked
+    lib.sbd_plan_cache_clear()

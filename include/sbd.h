@@ -18,7 +18,8 @@
  *    semantics).  With device pointers the work is enqueued on the plan's stream and the call
  *    returns immediately (use sbd_plan_sync / the stream to wait).
  *  - return value: 0 = ok, 1 = bad dimensions (the UM variant's `error = 1`, U:198-201),
- *    2 = invalid argument, 3 = CUDA failure (sbd_last_error() has the text).
+ *    2 = invalid argument, 3 = CUDA failure (sbd_last_error() has the text), 4 = a neighbour rank did not
+ *    deliver its halo rows in time (multi-GPU row blocks).
  *  - there is NO CPU fallback: without a usable CUDA device every entry point returns 3.
  *  - transcendental functions are the pinned algorithms of sbd_math.h (see there).
  *
@@ -39,6 +40,7 @@ extern "C" {
 #define SBD_EDIMS 1
 #define SBD_EINVAL 2
 #define SBD_ECUDA 3
+#define SBD_EPEER 4 /* multi-GPU: a neighbour rank never posted its halo rows (sbd_plan_set_peer_sync) */
 
 #define SBD_VARIANT_GENERIC 0 /* G / U: halo'd neighbour fields, 3-D p, windspeed updated every step */
 #define SBD_VARIANT_PYTHON 1  /* P / S: index-mapped boundaries, 1-D p, 6-hourly windspeed update    */
@@ -231,22 +233,22 @@ int sbd_plan_set_peer_theta(sbd_plan* plan, const float* theta_up, int ny_up, co
  * kernel posts its step sequence number into the neighbours' words and only the CTAs that read
  * neighbour rows wait for the neighbours' own post.  Every rank must issue the same number of
  * steps; a rank's theta plane of step k must stay untouched until its step k+1 has completed
- * (keep at least two theta planes and alternate).  A neighbour that never posts is reported in
- * sync_local[2], [3] after ~4 s instead of hanging the GPU.  NULL sync_local switches it off. */
+ * (keep at least two theta planes and alternate).  A neighbour that never posts is reported after ~4 s instead of
+ * hanging the GPU: the kernel leaves a marker in sync_local[2], [3], and sbd_plan_sync -- and every step call that
+ * synchronises because it was given host arrays -- then returns SBD_EPEER (the step's results are invalid).
+ * (Re-)arming clears this rank's four words and restarts the sequence: do it on every rank between two barriers.
+ * NULL sync_local switches the handshake off. */
 int sbd_plan_set_peer_sync(sbd_plan* plan, uint32_t* sync_local, uint32_t* sync_up, uint32_t* sync_dn);
-/* Pipelined steps for device-resident time loops (batched records, benchmarks): the window kernel
- * of step k+1 is launched as the programmatic dependent of step k's level scan and runs under it;
- * level scans of consecutive steps then follow each other without a gap.  Contract: the inputs of
- * a step (p, u, v, theta and, for the first step, the state arrays) must already be complete on
- * the device when the PREVIOUS sbd_plan_step call is issued, i.e. they must not be produced by
- * work enqueued between two step calls.  Results are bit-identical to the unpipelined step.
- * Steps with host pointers or with per-kernel timing enabled run unpipelined. */
-int sbd_plan_set_pipelined(sbd_plan* plan, int on);
-/* Form of the window-sum kernel: 0 = automatic (strip kernel when the largest search radius is
- * >= 9 cells, tile kernel below), 1 = tile kernel (one cell per thread, cells bucketed by radius),
- * 2 = strip kernel (four cells per thread share every shared-memory load, packed fp32 adds).
- * Both evaluate each cell's sums in the reference's raster order: identical bits. */
+/* Form of the window-sum kernel: 0 = automatic (tile kernel k_trigger for search radii <= 8, round 1's 4-cell strip
+ * kernel k_win4 for 9..31, the signed-class strip kernel k_win8 from 32), 1 = tile kernel (one cell per thread, cells
+ * bucketed by radius), 2 = k_win4, 3 = k_win8.  Every form evaluates each cell's sums in the reference's raster
+ * order: identical bits (tests force each form on every grid class). */
 int sbd_plan_set_window_kernel(sbd_plan* plan, int mode);
+/* Cells per strip of k_win8: 4 (default) or 8 (faster only where a tile's radii are nearly uniform). */
+int sbd_plan_set_strip_cells(sbd_plan* plan, int cells);
+/* Process-wide: 1 = evaluate the sigmoid statistics with the plain sequential chain (one warp) instead of the exact
+ * parallel formulation.  Same bits either way; kept as the in-library cross-check of the parallel form. */
+int sbd_set_stats_mode(int sequential);
 /* Restrict the trigger to rows [row_lo, row_hi) of the plan's grid (row_hi < 0: to the end); call before
  * sbd_plan_set_static.  Cells of other rows are treated like cells outside the coastal zone (missing
  * value, state untouched) but still serve as neighbours.  This is how the python variant -- whose

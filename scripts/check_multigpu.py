@@ -93,7 +93,7 @@ plan_f = generic.Plan(SBD_VARIANT_GENERIC, nx, nyl, nz, h)
 plan_f.set_halo_mode(ex.halo_mode())
 plan_f.set_static(mk, zh, sh, stats=stats)
 plan_f.set_peer_sync(*peer_f.sync_words())
-plan_f.set_pipelined(True)
+
 st_f = [torch.zeros((nyl, nx), dtype=torch.float32, device=dev) for _ in range(3)]
 sb_f = [torch.zeros((nyl, nx), dtype=torch.float32, device=dev) for _ in STEPS]
 torch.cuda.synchronize()

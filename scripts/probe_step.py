@@ -28,8 +28,6 @@ torch.cuda.synchronize()
 torch.cuda.set_stream(stream)
 plan.set_stream(stream.cuda_stream)
 plan.set_static(mk, zh, sh)
-if os.environ.get("PROBE_PIPE"):
-    plan.set_pipelined(True)
 print(plan.info())
 flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 flags = torch.zeros((ny, nx), dtype=torch.uint8, device=dev) if os.environ.get("PROBE_FLAGS") else None

@@ -855,13 +855,6 @@ struct TrigArgs {
   const float* theta_up; const float* theta_dn;
   int ny_up;  // interior rows of the northern neighbour's block
   int order;  // 0: scan -> window -> final (multi-GPU friendly); 1: window -> scan(+thresholds)
-  // Pipelined steps (sbd_plan_set_pipelined, order 1 only): the window kernel of step k+1 is the
-  // programmatic dependent of the level scan of step k and runs under it.  It therefore must not
-  // touch anything scan k still reads or writes: n_thc goes to one of two plan-owned scratch planes
-  // (thc_scr) and the scan's epilogue stores it into the caller's thc array (G:262).
-  int pipe;
-  float* thc_scr;
-  unsigned* pipe_ctr;  // CTAs of the window kernel that have finished (pipelined steps)
   // Multi-GPU row blocks without a separate barrier launch: sync_local[0] / [1] are written by the
   // northern / southern neighbour rank ("my theta plane of step sync_seq is in place"); this rank
   // posts sync_seq into sync_up[1] and sync_dn[0].  Only CTAs that read neighbour rows wait.
@@ -1192,9 +1185,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
   const int tid = threadIdx.x;
 
   // order 1: the level scan follows as a programmatic dependent and may start right away.
-  // Pipelined: this grid itself runs under the PREVIOUS step's scan; its own scan is released at
-  // the very end, once that previous scan has completed (see the end of the kernel).
-  if (SPLIT && a.order == 1 && !a.pipe) asm volatile("griddepcontrol.launch_dependents;");
+  if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
 
   if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {
     // multi-GPU: tell the neighbours that this rank's theta of this step is in place (the plane
@@ -1399,8 +1390,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
       // generic: n_thc goes straight into the caller's thc array (state update G:262); the
       // thresholds are applied by k_final once the level scan has delivered n_ws / n_wd.  This
       // grid never waits for the scan, so its CTAs retire while the scan is still streaming.
-      // (pipelined: the previous step's scan may still be reading thc -> scratch plane)
-      (a.pipe ? a.thc_scr : a.thc)[c] = n_thc;
+      a.thc[c] = n_thc;
     } else if (VARIANT == SBD_VARIANT_PYTHON) {
       const int lev = s_lev;
       const float uu = __ldg(a.u + (size_t)lev * n2 + c), vv = __ldg(a.v + (size_t)lev * n2 + c);
@@ -1429,21 +1419,6 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
       wind_from_uv(a, uu, vv, n_ws, n_wd);
       a.thc[c] = n_thc;
       trigger_point<VARIANT>(a, c, n2, n_thc, n_ws, n_wd, 0.0f);
-    }
-  }
-  if (SPLIT && a.pipe) {
-    // pipelined: this step's scan may start only when the previous step's scan has completed
-    // (state arrays, the other scratch plane).  CTAs just exit -- an exited CTA counts as having
-    // released the dependents, and its SM resources go to the CTAs still to come -- except the one
-    // that finishes last: it waits for the previous scan and then releases this step's scan.  So
-    // "this grid complete" implies "previous scan complete" for the dependent's own wait.
-    if (tid == 0) {
-      const unsigned n_cta = gridDim.x * gridDim.y;
-      if (atomicAdd(a.pipe_ctr, 1u) == n_cta - 1u) {
-        *a.pipe_ctr = 0u;  // the next window kernel cannot start before the release below
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        asm volatile("griddepcontrol.launch_dependents;");
-      }
     }
   }
 }
@@ -1518,7 +1493,7 @@ __device__ __forceinline__ void finish_cell(const TrigArgs& a, int gx, int gy, b
   const float mul = land_c ? 1.0f : -1.0f;                    // G:182-186
   const float n_thc = mul * ((T_l / n_l) - (T_s / n_s));      // G:216
   if (SPLIT) {
-    (a.pipe ? a.thc_scr : a.thc)[c] = n_thc;                  // G:262; thresholds follow in the scan / k_final
+    a.thc[c] = n_thc;                  // G:262; thresholds follow in the scan / k_final
   } else if (VARIANT == SBD_VARIANT_PYTHON) {
     const int so = own_index<VARIANT>(a.g, gx, gy);
     const float uu = __ldg(a.u + (size_t)s_lev * n2 + c), vv = __ldg(a.v + (size_t)s_lev * n2 + c);
@@ -1573,7 +1548,7 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
-  if (SPLIT && a.order == 1 && !a.pipe) asm volatile("griddepcontrol.launch_dependents;");
+  if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
 
   if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {  // multi-GPU post / wait, as in k_trigger
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
@@ -1840,20 +1815,9 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
     finish_cell<VARIANT, SPLIT>(a, gx, gy, (b & 0x80u) != 0, T_l, T_s, c_l, c_s, s_lev);
   }
 
-  if (SPLIT && a.pipe) {  // pipelined steps: see the end of k_trigger
-    if (tid == 0) {
-      const unsigned n_cta = gridDim.x * gridDim.y;
-      if (atomicAdd(a.pipe_ctr, 1u) == n_cta - 1u) {
-        *a.pipe_ctr = 0u;
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        asm volatile("griddepcontrol.launch_dependents;");
-      }
-    }
-  }
 }
 
 #include "sbd_win8.cuh"
-#include "sbd_wsmall.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K4b level scan, scalar form (generic variant; used when nx*ny is not a multiple of 4, p is not
@@ -1906,155 +1870,19 @@ __global__ void __launch_bounds__(256) k_scan_scalar(const TrigArgs a, const int
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4b', the vectorised form of k_scan_scalar: one thread per aligned QUAD of cells (linear
-// indices 4m..4m+3, at least one of them in the coastal zone), compacted in raster order.  Each
-// level of the four pressure columns arrives as one 16-byte copy; the per-cell first-minimum
-// search and the wind at the selected level are exactly those of k_scan_scalar.
-// Needs nx*ny % 4 == 0 and 16-byte aligned p.
+// K4b', the vectorised form of k_scan_scalar: one thread per aligned QUAD of cells (linear indices
+// 4m..4m+3, at least one of them in the coastal zone), compacted in raster order.  Each level of the
+// four pressure columns arrives as one 16-byte streaming load; B levels are requested with B independent
+// loads (asm volatile keeps them together ahead of the compares), no shared memory.  The per-cell
+// first-minimum search and the wind at the selected level are exactly those of k_scan_scalar.
+// Needs nx*ny % 4 == 0 and 16-byte aligned p, u, v.
+// Measured (scripts/mb_scan.cu, profiles/r2_mb_scan.txt): ~35 us for the c2 access pattern with any B from 5 to
+// 18, any block size, with the levels split over 2-8 threads per quad, or staged through shared memory with
+// cp.async (round 1's k_scan_quad, removed) -- the same 35 us a dense read of the whole 220 MB array takes: the
+// cost follows the 128-byte lines touched, and runs of ~16 coastal cells touch 97 % of them.  In the step, beside
+// the window kernel, B = 5 was best (few registers keep enough scan CTAs resident): B = 2..14 gave
+// 57.6 / 46.6 / 45.0 / 43.6 / 44.7 / 46.0 / 47.3 us per step.
 // ------------------------------------------------------------------------------------------------
-// The columns are staged through shared memory with cp.async (LDGSTS): a thread issues G
-// 16-byte copies per group without holding registers for them, two groups are in flight per
-// thread (2*G*16 B = 448 B), and each thread only ever reads back its own slots, so the kernel
-// needs no block barrier at all.
-template <int G, int NT>
-__global__ void __launch_bounds__(NT) k_scan_quad(const TrigArgs a, const int* __restrict__ quads,
-                                                  int n_quads)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* s_buf = reinterpret_cast<float4*>(smem_raw);  // [2][G][NT]
-  const int tid = threadIdx.x;
-  const int i = blockIdx.x * NT + tid;
-  if (i >= n_quads) return;
-  const int m = quads[i];
-  const int c0 = m * 4;
-  const size_t n2 = (size_t)a.g.nx * a.g.ny;
-  const size_t stride4 = n2 >> 2;
-  const float tp = a.prm.target_plev;
-  const int nz = a.nz;
-  const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
-  const int ngroups = (nz + G - 1) / G;
-
-  // p is streamed exactly once: mark its lines evict-first in L2 so that the small planes the
-  // window kernel re-reads every step (gzsm, code, state, scratch) stay resident beside the stream
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  auto issue = [&](int g) {
-    float4* dst = s_buf + (size_t)((g & 1) * G) * NT + tid;
-    const int kbase = g * G;
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      if (kbase + j < nz) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)j * NT);
-        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa),
-                     "l"(pq + (size_t)(kbase + j) * stride4), "l"(pol)
-                     : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
-
-  issue(0);
-  // order 0: the window kernel launched next in the stream may start now (programmatic dependent)
-  if (a.order == 0) asm volatile("griddepcontrol.launch_dependents;");
-  // Everything the epilogue needs that does not depend on the scan is requested now, so that it
-  // arrives under the pressure stream: which cells of the quad are coastal (static code plane),
-  // and (order 1) the previous windspeed / winddir of the quad as 16-byte loads.
-  uint32_t cdq[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + j;
-    const int y = c / a.g.nx, x = c - y * a.g.nx;
-    cdq[j] = a.code[(size_t)(y + a.g.h) * a.g.ldx + (x + a.g.h)];
-  }
-  float4 ws4 = make_float4(0.f, 0.f, 0.f, 0.f), wd4 = ws4;
-  if (a.order == 1 && !a.first_step) {
-    ws4 = __ldcg(reinterpret_cast<const float4*>(a.ws) + m);
-    wd4 = __ldcg(reinterpret_cast<const float4*>(a.wd) + m);
-  }
-  float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
-  int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-  int pf_lev = -1;
-  for (int g = 0; g < ngroups; ++g) {
-    if (g + 1 < ngroups) {
-      issue(g + 1);
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
-    const float4* src = s_buf + (size_t)((g & 1) * G) * NT + tid;
-    const int kbase = g * G;
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      const int kk = kbase + j;
-      if (kk < nz) {
-        const float4 d = src[(size_t)j * NT];
-        const float e0 = fabsf(d.x - tp), e1 = fabsf(d.y - tp), e2 = fabsf(d.z - tp), e3 = fabsf(d.w - tp);
-        // minloc(abs(p - target_plev)): level 0 initialises, later levels need a strict < (G:223)
-        if (kk == 0 || e0 < b0) { b0 = e0; l0 = kk; }
-        if (kk == 0 || e1 < b1) { b1 = e1; l1 = kk; }
-        if (kk == 0 || e2 < b2) { b2 = e2; l2 = kk; }
-        if (kk == 0 || e3 < b3) { b3 = e3; l3 = kk; }
-      }
-    }
-    // speculative L2 prefetch of u,v at the best level so far: for a monotone pressure column the
-    // minimum is final long before the last group, and the epilogue's loads then hit L2
-    if (l0 != pf_lev) {
-      pf_lev = l0;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(a.u + (size_t)l0 * n2) + m));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(a.v + (size_t)l0 * n2) + m));
-    }
-  }
-  bool act[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) act[j] = (cdq[j] & 0x7fffu) != 0;
-  // wind at the selected levels: all loads first
-  const int lv[4] = {l0, l1, l2, l3};
-  float uu[4], vv[4];
-  if (l0 == l1 && l1 == l2 && l2 == l3) {  // the usual case: one 16-byte load each
-    const float4 u4 = __ldcs(reinterpret_cast<const float4*>(a.u + (size_t)l0 * n2) + m);
-    const float4 v4 = __ldcs(reinterpret_cast<const float4*>(a.v + (size_t)l0 * n2) + m);
-    uu[0] = u4.x; uu[1] = u4.y; uu[2] = u4.z; uu[3] = u4.w;
-    vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uu[j] = __ldcs(a.u + (size_t)lv[j] * n2 + c0 + j);
-      vv[j] = __ldcs(a.v + (size_t)lv[j] * n2 + c0 + j);
-    }
-  }
-  float nws[4], nwd[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) wind_from_uv(a, uu[j], vv[j], nws[j], nwd[j]);
-  if (a.order == 1) {
-    // this grid is the programmatic dependent of the window kernel: wait for its n_thc, then
-    // thresholds, scaling and state update right here (G:235-266) -- no further kernel
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.thc) + m);
-    const float thc_[4] = {thc4.x, thc4.y, thc4.z, thc4.w};
-    const float wsp[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
-    const float wdp[4] = {wd4.x, wd4.y, wd4.z, wd4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (act[j]) trigger_point_vals(a, (size_t)(c0 + j), thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
-    return;
-  }
-  if (act[0] && act[1] && act[2] && act[3]) {
-    reinterpret_cast<float4*>(a.nws)[m] = make_float4(nws[0], nws[1], nws[2], nws[3]);
-    reinterpret_cast<float4*>(a.nwd)[m] = make_float4(nwd[0], nwd[1], nwd[2], nwd[3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (act[j]) { a.nws[c0 + j] = nws[j]; a.nwd[c0 + j] = nwd[j]; }
-  }
-}
-
-// Register form of k_scan_quad: B levels of the quad's four columns are requested with B
-// independent 16-byte loads (asm volatile keeps them together ahead of the compares), no shared
-// memory at all.  Measured with scripts/mb_scan.cu: ~35 us for the c2 access pattern against
-// ~37-38 us for the cp.async form; in the step (c2, beside the window kernel) B = 5 is best:
-// 43.6 us per step (B=2: 57.6, 3: 46.6, 4: 45.0, 5: 43.6, 7: 44.7, 10: 46.0, 14: 47.3; cp.async form
-// 50.5) -- few registers per thread keep enough scan CTAs resident while the window kernel runs.
-// SBD_SCAN_REGS=<B> selects the batch, SBD_SCAN_REGS=0 the cp.async kernel.
 template <int B, int NT>
 __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const int* __restrict__ quads,
                                                        int n_quads)
@@ -2068,9 +1896,8 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
   const float tp = a.prm.target_plev;
   const int nz = a.nz;
   const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
-  // order 0: the window kernel follows as a dependent.  Pipelined order 1: the NEXT step's window
-  // kernel does, and may run under this scan (it touches nothing this grid reads or writes).
-  if (a.order == 0 || a.pipe) asm volatile("griddepcontrol.launch_dependents;");
+  // order 0: the window kernel follows as a dependent and may start now
+  if (a.order == 0) asm volatile("griddepcontrol.launch_dependents;");
   uint32_t cdq[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -2138,16 +1965,13 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
     // this grid is the programmatic dependent of the window kernel: wait for its n_thc, then
     // thresholds, scaling and state update right here (G:235-266) -- no further kernel
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.pipe ? a.thc_scr : a.thc) + m);
+    const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.thc) + m);
     const float thc_[4] = {thc4.x, thc4.y, thc4.z, thc4.w};
     const float wsp[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
     const float wdp[4] = {wd4.x, wd4.y, wd4.z, wd4.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (act[j]) {
-        if (a.pipe) a.thc[c0 + j] = thc_[j];  // state update G:262 (the window kernel wrote a scratch plane)
-        trigger_point_vals(a, (size_t)(c0 + j), thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
-      }
+      if (act[j]) trigger_point_vals(a, (size_t)(c0 + j), thc_[j], nws[j], nwd[j], wsp[j], wdp[j]);
     return;
   }
   if (act[0] && act[1] && act[2] && act[3]) {
@@ -2160,258 +1984,7 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
   }
 }
 
-#include "sbd_stepq.cuh"
-
 // ------------------------------------------------------------------------------------------------
-// K4 fused step (generic variant, coarse grids): ONE launch per timestep.  A CTA owns a 64x16-cell
-// tile and splits into two roles that run side by side on the same SM:
-//   warps 0..7  (256 threads)  window role: stage t0 + land bits of the tile and its halo, bucket
-//                               the coastal cells by nn, sequential window sums -> n_thc (as k_trigger)
-//   warps 8..11 (128 threads)  scan role:   the tile's 256 aligned quads, two per thread, pressure
-//                               columns streamed with cp.async (G levels x 2 groups x 2 quads in
-//                               flight per thread), first minimum of |p - target|, u,v at that level
-//                               -> n_ws, n_wd (as k_scan_quad)
-// The scan warps are almost always stalled on HBM, the window warps on shared memory / issue
-// slots, so the two overlap on every SM by construction (no second launch, no dependent-launch
-// scheduling, no scratch planes).  The roles meet at one block barrier; then all 384 threads apply
-// thresholds, scaling and the state update (G:235-266) to the tile's coastal cells.
-// Needs nx % 4 == 0, 16-byte aligned p,u,v and R <= RMAX.
-// ------------------------------------------------------------------------------------------------
-template <int TX, int TY, int RMAX, int G>
-__global__ void __launch_bounds__(384, 3) k_step_fused(const TrigArgs a)
-{
-  constexpr int NWIN = 256, NSCAN = 128, NTHR = NWIN + NSCAN;
-  constexpr int NCELL = TX * TY, NQ = NCELL / 4, QPT = NQ / NSCAN, QROW = TX / 4;
-  constexpr int CPT = NCELL / NWIN;
-  constexpr int NB = 64;
-  constexpr int VARIANT = SBD_VARIANT_GENERIC;
-  static_assert(QPT == 2 && TX % 32 == 0 && NCELL % NWIN == 0 && NWIN % TX == 0, "tile shape");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int R = a.R;
-  const int W = TX + 2 * R, Hh = TY + 2 * R;
-  const int total = W * Hh;
-  const int WBW = (W + 31) >> 5, WBITS = WBW * 32;
-  float4* s_buf = reinterpret_cast<float4*>(smem_raw);                 // [2][G][NSCAN]
-  float* s_thc = reinterpret_cast<float*>(s_buf + 2 * G * NSCAN);        // [NCELL]
-  float* s_nws = s_thc + NCELL;
-  float* s_nwd = s_nws + NCELL;
-  uint32_t* s_list = reinterpret_cast<uint32_t*>(s_nwd + NCELL);        // [NCELL]
-  float* s_t0 = reinterpret_cast<float*>(s_list + NCELL);               // [total]
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_t0 + total);         // [Hh*WBW + 2]
-  __shared__ int s_cnt[NB];
-  __shared__ int s_off[NB];
-  __shared__ int s_nlist;
-  __shared__ uint16_t s_qlist[NQ];   // scan role: local ids of the tile's quads with a coastal cell
-
-  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-  const int tid = threadIdx.x;
-  const size_t n2 = (size_t)a.g.nx * a.g.ny;
-
-  if (tid >= NWIN) {
-    // ============================== scan role ==============================
-    // 1. compact the tile's quads that hold a coastal cell; 2. warps pull chunks of 32 quads from
-    //    that list, one quad per lane, G levels x 2 groups in flight per lane.
-    const int st = tid - NWIN;
-    const int lane = st & 31;
-    const float tp = a.prm.target_plev;
-    const int nz = a.nz;
-    const size_t stride4 = n2 >> 2;
-    const int ngroups = (nz + G - 1) / G;
-    // every scan warp owns 64 consecutive quads of the tile (4 tile rows) and compacts the ones with
-    // a coastal cell into its own slice of s_qlist: warp-local, no block-level synchronisation
-    const int sw = st >> 5;
-    int nact = 0;
-#pragma unroll
-    for (int q = 0; q < QPT; ++q) {
-      const int lq = sw * (NQ / 4) + q * 32 + lane;
-      const int ly = lq / QROW, lxq = lq - ly * QROW;
-      const int gx0 = x0 + lxq * 4, gy = y0 + ly;
-      bool anyc = false;
-      if (gx0 < a.g.nx && gy < a.g.ny) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          anyc |= (a.code[(size_t)(gy + a.g.h) * a.g.ldx + (gx0 + j + a.g.h)] & 0x7fffu) != 0;
-      }
-      const uint32_t bal = __ballot_sync(0xffffffffu, anyc);
-      if (anyc) s_qlist[sw * (NQ / 4) + nact + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)lq;
-      nact += __popc(bal);
-    }
-    __syncwarp();
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    for (int chunk = 0; chunk < nact; chunk += 32) {
-      const int ent = chunk + lane;
-      const bool have = ent < nact;
-      const int lq = have ? (int)s_qlist[sw * (NQ / 4) + ent] : 0;
-      const int ly = lq / QROW, lxq = lq - ly * QROW;
-      const int c0 = (y0 + ly) * a.g.nx + x0 + lxq * 4;
-      const int m = c0 >> 2;
-      const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
-      auto issue = [&](int g) {
-        const int kbase = g * G;
-        if (have) {
-          float4* dst = s_buf + (size_t)((g & 1) * G) * NSCAN + st;
-#pragma unroll
-          for (int j = 0; j < G; ++j) {
-            if (kbase + j < nz) {
-              const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)j * NSCAN);
-              asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa),
-                           "l"(pq + (size_t)(kbase + j) * stride4), "l"(pol)
-                           : "memory");
-            }
-          }
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-      };
-      issue(0);
-      float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
-      int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-      for (int g = 0; g < ngroups; ++g) {
-        if (g + 1 < ngroups) {
-          issue(g + 1);
-          asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        } else {
-          asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        }
-        if (have) {
-          const float4* src = s_buf + (size_t)((g & 1) * G) * NSCAN + st;
-          const int kbase = g * G;
-#pragma unroll
-          for (int j = 0; j < G; ++j) {
-            const int kk = kbase + j;
-            if (kk < nz) {
-              const float4 d = src[(size_t)j * NSCAN];
-              const float e0 = fabsf(d.x - tp), e1 = fabsf(d.y - tp), e2 = fabsf(d.z - tp), e3 = fabsf(d.w - tp);
-              // minloc(abs(p - target_plev)): level 0 initialises, later levels need a strict < (G:223)
-              if (kk == 0 || e0 < b0) { b0 = e0; l0 = kk; }
-              if (kk == 0 || e1 < b1) { b1 = e1; l1 = kk; }
-              if (kk == 0 || e2 < b2) { b2 = e2; l2 = kk; }
-              if (kk == 0 || e3 < b3) { b3 = e3; l3 = kk; }
-            }
-          }
-        }
-      }
-      if (have) {
-        // wind at the selected levels (G:225-227) -> shared memory
-        const int lv[4] = {l0, l1, l2, l3};
-        float uu[4], vv[4];
-        if (l0 == l1 && l1 == l2 && l2 == l3) {
-          const float4 u4 = __ldcs(reinterpret_cast<const float4*>(a.u + (size_t)l0 * n2) + m);
-          const float4 v4 = __ldcs(reinterpret_cast<const float4*>(a.v + (size_t)l0 * n2) + m);
-          uu[0] = u4.x; uu[1] = u4.y; uu[2] = u4.z; uu[3] = u4.w;
-          vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uu[j] = __ldcs(a.u + (size_t)lv[j] * n2 + c0 + j);
-            vv[j] = __ldcs(a.v + (size_t)lv[j] * n2 + c0 + j);
-          }
-        }
-        const int lbase = ly * TX + lxq * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float n_ws, n_wd;
-          wind_from_uv(a, uu[j], vv[j], n_ws, n_wd);
-          s_nws[lbase + j] = n_ws;
-          s_nwd[lbase + j] = n_wd;
-        }
-      }
-    }
-  } else {
-    // ============================== window role ==============================
-    if (tid < NB) s_cnt[tid] = 0;
-    {
-      constexpr int MAXC = (TX + 2 * RMAX + 31) / 32;
-      const int warp = tid >> 5, lane = tid & 31;
-      for (int ly = warp; ly < Hh; ly += NWIN / 32) {
-        float th[MAXC], gz[MAXC];
-        uint32_t cd[MAXC];
-#pragma unroll
-        for (int cch = 0; cch < MAXC; ++cch) {
-          const int lx = cch * 32 + lane;
-          th[cch] = 0.0f; gz[cch] = 0.0f; cd[cch] = 0u;
-          if (lx < W) {
-            const int sidx = nbr_index<VARIANT>(a.g, x0 - R + lx, y0 - R + ly);
-            th[cch] = load_theta<VARIANT>(a, x0 - R + lx, y0 - R + ly, sidx);
-            gz[cch] = a.gzsm[sidx];
-            cd[cch] = a.code[sidx];
-          }
-        }
-#pragma unroll
-        for (int cch = 0; cch < MAXC; ++cch) {
-          const int lx = cch * 32 + lane;
-          if (lx < W) s_t0[ly * W + lx] = th[cch] - gz[cch];  // G:167
-          const uint32_t bb = __ballot_sync(0xffffffffu, (cd[cch] >> 15) != 0);
-          if (lane == 0 && cch * 32 < WBITS) s_bits[ly * WBW + cch] = bb;
-        }
-      }
-      if (tid < 2) s_bits[Hh * WBW + tid] = 0u;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int cx = tid % TX;
-    const int cy0 = (tid / TX) * CPT;
-    uint32_t my_code[CPT];
-    int my_slot[CPT];
-#pragma unroll
-    for (int q = 0; q < CPT; ++q) {
-      const int gx = x0 + cx, gy = y0 + cy0 + q;
-      my_code[q] = 0;
-      my_slot[q] = -1;
-      if (gx >= a.g.nx || gy >= a.g.ny) continue;
-      const uint32_t cd = a.code[own_index<VARIANT>(a.g, gx, gy)];
-      const int nn = (int)(cd & 0x7fffu);
-      my_code[q] = cd;
-      if (nn == 0) {  // outside the coastal zone (G:174-176)
-        const size_t c = (size_t)gy * a.g.nx + gx;
-        a.sb[c] = a.prm.missing;
-        if (a.flags) a.flags[c] = 0;
-      } else {
-        const int bkt = (nn <= R && nn < NB - 1) ? nn : NB - 1;
-        my_slot[q] = atomicAdd(&s_cnt[bkt], 1);
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (tid == 0) {
-      int run = 0;
-      for (int k = 0; k < NB; ++k) { s_off[k] = run; run += s_cnt[k]; }
-      s_nlist = run;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll
-    for (int q = 0; q < CPT; ++q) {
-      if (my_slot[q] >= 0) {
-        const int nn = (int)(my_code[q] & 0x7fffu);
-        const int bkt = (nn <= R && nn < NB - 1) ? nn : NB - 1;
-        const int lid = (cy0 + q) * TX + cx;
-        s_list[s_off[bkt] + my_slot[q]] = ((my_code[q] & 0x8000u) << 16) | ((uint32_t)bkt << 16) | (uint32_t)lid;
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int n_list = s_nlist;
-    for (int e = tid; e < n_list; e += NWIN) {
-      const uint32_t ent = s_list[e];
-      const int lid = (int)(ent & 0xffffu);
-      const int ly = lid / TX, lx = lid - ly * TX;
-      const int gx = x0 + lx, gy = y0 + ly;
-      const int so = own_index<VARIANT>(a.g, gx, gy);
-      s_thc[lid] = cell_thc<VARIANT, NB>(a, s_t0, s_bits, W, WBITS, R, ent, lx, ly, gx, gy, so);
-    }
-  }
-  __syncthreads();
-  // ============================== thresholds: all threads ==============================
-  const int n_list = s_nlist;
-  for (int e = tid; e < n_list; e += NTHR) {
-    const int lid = (int)(s_list[e] & 0xffffu);
-    const int ly = lid / TX, lx = lid - ly * TX;
-    const size_t c = (size_t)(y0 + ly) * a.g.nx + (x0 + lx);
-    const float n_thc = s_thc[lid];
-    a.thc[c] = n_thc;                                                     // G:262
-    float wsp = 0.0f, wdp = 0.0f;
-    if (!a.first_step) { wsp = __ldcg(a.ws + c); wdp = __ldcg(a.wd + c); }
-    trigger_point_vals(a, c, n_thc, s_nws[lid], s_nwd[lid], wsp, wdp);
-  }
-}
-
 // K4c final: thresholds, scaling and state update (G:235-266) for every coastal-zone cell of the
 // compacted list, from n_thc (thc[], window kernel) and n_ws / n_wd (scratch planes, scan kernel).
 // An ordinary (fully stream-ordered) launch: it must see both the scan's and the window kernel's
@@ -2441,11 +2014,6 @@ struct QuadFlag {
     }
     return any;
   }
-};
-
-struct QuadOffFlag {
-  QuadFlag f;
-  __host__ __device__ __forceinline__ bool operator()(const int& m) const { return !f(m); }
 };
 
 // flag functor for the compaction of coastal-zone cells (interior, raster order)
@@ -2512,6 +2080,7 @@ struct sbd_plan {
   uint16_t* d_code = nullptr;
   uint32_t* d_cl = nullptr;   // land cells in every coastal-zone cell's final window (k_static_counts)
   int row_lo = 0, row_hi = -1;  // sbd_plan_set_row_window (-1: to the end)
+  int strip_cells = 4;        // sbd_plan_set_strip_cells: cells per strip of k_win8 (4 or 8)
   int window_kernel = 0;      // sbd_plan_set_window_kernel: 0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4)
   float* d_stats = nullptr;   // 4 floats
   float* d_carry = nullptr;   // 5 floats
@@ -2524,8 +2093,6 @@ struct sbd_plan {
   unsigned long long* d_sum = nullptr;
   unsigned long long static_sum[6] = {0, 0, 0, 0, 0, 0};
   bool sum_valid = false;
-  int* d_quads_off = nullptr; // ... and of the quads holding none (k_step_quad fills their sb_con)
-  int n_quads_off = 0;
   void* d_cub = nullptr;      // cub temp storage
   size_t cub_bytes = 0;
   float* d_nws = nullptr;     // scratch: wind speed at the selected level (scan -> window kernel)
@@ -2542,10 +2109,6 @@ struct sbd_plan {
   int peer_ny_up = 0;
   uint32_t *sync_local = nullptr, *sync_up = nullptr, *sync_dn = nullptr;  // sbd_plan_set_peer_sync
   uint32_t sync_seq = 0;
-  bool pipelined = false;     // sbd_plan_set_pipelined
-  float* d_thc_scr[2] = {nullptr, nullptr};
-  unsigned* d_pipe_ctr = nullptr;
-  unsigned pipe_seq = 0;
   const float *cur_p = nullptr, *cur_u = nullptr, *cur_v = nullptr;
   // optional per-kernel CUDA-event timing of the step (bench.py roofline leg)
   bool timing = false;
@@ -2588,15 +2151,9 @@ int stage_get(sbd_plan* p, size_t bytes, void** out)
 // Pinned (page-locked, device-mapped) host memory can be read by the kernels in place over PCIe.
 // The level scan touches only the pressure columns of coastal-zone cells and one level of u,v,
 // so for these large 3-D arrays a zero-copy gather moves a fraction of the bytes a staged copy
-// would.  SBD_ZERO_COPY=0 disables it.
+// would.
 const float* mapped_host_ptr(const float* src)
 {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("SBD_ZERO_COPY");
-    enabled = (e && atoi(e) == 0) ? 0 : 1;
-  }
-  if (!enabled) return nullptr;
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, src) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   if (at.type == cudaMemoryTypeHost && at.devicePointer) return (const float*)at.devicePointer;
@@ -2634,18 +2191,24 @@ int out_view(sbd_plan* p, void* dst, size_t bytes, bool copy_in, void** dev, std
 int flush_out(sbd_plan* p, std::vector<OutView>& pend, bool any_host)
 {
   for (auto& o : pend) CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, p->stream));
-  if (any_host || !pend.empty()) CK(cudaStreamSynchronize(p->stream));
+  if (any_host || !pend.empty()) {
+    CK(cudaStreamSynchronize(p->stream));
+    if (p->sync_local) {
+      uint32_t mark[2] = {0u, 0u};
+      CK(cudaMemcpy(mark, p->sync_local + 2, sizeof mark, cudaMemcpyDeviceToHost));
+      if (mark[0] || mark[1]) return fail(SBD_EPEER, "neighbour rank did not post its theta plane within 4 s; results are invalid");
+    }
+  }
   return SBD_OK;
 }
 
-// SBD_STATS_SEQ=1 selects the plain sequential chain (k_stats_seq) instead of the exact parallel
-// formulation (k_stats_exact); both produce the reference's bits, the tests compare them.
+// The exact parallel formulation (k_stats_exact) is what runs; the plain sequential chain (k_stats_seq) is kept as
+// its in-library cross-check: sbd_set_stats_mode(1) selects it, tests compare the two bit for bit.
+std::atomic<int> g_stats_seq{0};
 void launch_stats_pass(cudaStream_t st, const float* d_ary, int nx, int ny, int ld, int pass, int first,
                        float* d_carry)
 {
-  static int seq = -1;
-  if (seq < 0) { const char* e = getenv("SBD_STATS_SEQ"); seq = (e && atoi(e)) ? 1 : 0; }
-  if (seq) k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, pass, first, d_carry);
+  if (g_stats_seq.load()) k_stats_seq<<<1, 32, 0, st>>>(d_ary, nx, ny, ld, pass, first, d_carry);
   else k_stats_exact<<<1, ST_NT, 0, st>>>(d_ary, nx, ny, ld, pass, first, d_carry);
   LAUNCHED();
 }
@@ -2711,62 +2274,6 @@ bool scan_vec_ok(const sbd_plan* p, const TrigArgs& a)
          (((uintptr_t)a.u) & 15) == 0 && (((uintptr_t)a.v) & 15) == 0;
 }
 
-template <int G, int QNT>
-int launch_scan_quad(sbd_plan* p, const TrigArgs& a, int qsmem, bool pdl, int q0, int q1)
-{
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cdiv(q1 - q0, QNT));
-  cfg.blockDim = dim3(QNT);
-  cfg.dynamicSmemBytes = qsmem;
-  cfg.stream = p->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  const int* quads = p->d_quads + q0;
-  int nq = q1 - q0;
-  CK(cudaLaunchKernelEx(&cfg, k_scan_quad<G, QNT>, a, quads, nq));
-  return SBD_OK;
-}
-
-// the whole generic step as one kernel (k_step_quad, sbd_stepq.cuh): quads [q0, q1) of the compacted list,
-// fill = also set sb_con of the quads that hold no coastal-zone cell
-bool stepq_ok(const sbd_plan* p, const TrigArgs& a)
-{
-  auto al = [](const void* q, uintptr_t m) { return (((uintptr_t)q) & m) == 0; };
-  return p->variant == SBD_VARIANT_GENERIC && p->n_quads > 0 && p->nn_max <= 8 && (p->nx % 4) == 0 &&
-         a.prm.level_scan == 0 && al(a.p, 15) && al(a.u, 15) && al(a.v, 15) && al(a.ws, 15) && al(a.wd, 15) &&
-         al(a.thc, 15) && al(a.sb, 15) && al(a.flags, 3);
-}
-int launch_stepq(sbd_plan* p, const TrigArgs& a, int q0, int q1, bool fill)
-{
-  constexpr int NT = 128, B = 5;
-  const int nq = q1 - q0, noff = fill ? p->n_quads_off : 0;
-  const int nb = cdiv(nq, NT) + cdiv(noff, NT);
-  if (p->timing) { CK(cudaEventRecord(p->ev[0], p->stream)); CK(cudaEventRecord(p->ev[1], p->stream)); CK(cudaEventRecord(p->ev[2], p->stream)); }
-  static int minb = -1;   // resident CTAs per SM the kernel is compiled for: 6 (80 registers, default) or 4 (116)
-  if (minb < 0) { const char* e = getenv("SBD_STEPQ_MINB"); minb = e ? atoi(e) : 6; }
-  if (nb > 0) {
-    if (minb == 4) k_step_quad<B, NT, 4><<<nb, NT, 0, p->stream>>>(a, p->d_quads + q0, nq, p->d_quads_off, noff);
-    else k_step_quad<B, NT, 6><<<nb, NT, 0, p->stream>>>(a, p->d_quads + q0, nq, p->d_quads_off, noff);
-    LAUNCHED();
-  }
-  if (p->timing) CK(cudaEventRecord(p->ev[3], p->stream));
-  CK(cudaGetLastError());
-  return SBD_OK;
-}
-
-// which form of the quad scan runs: SBD_SCAN_REGS = B (levels in flight per thread, register form,
-// default 5) or 0 (cp.async form staged through shared memory)
-int scan_regs_setting()
-{
-  static int use_regs = -1;
-  if (use_regs < 0) { const char* e = getenv("SBD_SCAN_REGS"); use_regs = e ? atoi(e) : 5; }
-  return use_regs;
-}
-bool scan_uses_regs() { return scan_regs_setting() != 0; }
-
 // q0, q1: range of the compacted quad list to process (default: all of it)
 int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false, int q0 = 0, int q1 = -1)
 {
@@ -2777,37 +2284,8 @@ int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false, int q0 = 0, int q1 =
   if (p->n_coastal > 0) {
     const bool vec = scan_vec_ok(p, a);
     if (vec) {
-      constexpr int QNT = 128;
-      static int G = 0;
-      if (!G) {
-        const char* e = getenv("SBD_SCAN_G");
-        G = e ? atoi(e) : 10;
-        if (G != 5 && G != 7 && G != 10 && G != 14) G = 10;
-        CK(cudaFuncSetAttribute(k_scan_quad<5, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 5 * QNT * 16));
-        CK(cudaFuncSetAttribute(k_scan_quad<7, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 7 * QNT * 16));
-        CK(cudaFuncSetAttribute(k_scan_quad<10, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 10 * QNT * 16));
-        CK(cudaFuncSetAttribute(k_scan_quad<14, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 14 * QNT * 16));
-      }
-      // Shared memory per scan CTA also sets how many of them an SM holds, i.e. how much room is
-      // left for the window kernel's CTAs that run beside them (programmatic dependent launch).
-      static int pad_kb = -1;
-      if (pad_kb < 0) { const char* e = getenv("SBD_SCAN_SMEM_KB"); pad_kb = e ? atoi(e) : 0; }
-      int qsmem = 2 * G * QNT * 16;
-      if (pad_kb * 1024 > qsmem) {
-        qsmem = pad_kb * 1024;
-        static bool once = false;
-        if (!once) {
-          once = true;
-          CK(cudaFuncSetAttribute(k_scan_quad<5, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
-          CK(cudaFuncSetAttribute(k_scan_quad<7, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
-          CK(cudaFuncSetAttribute(k_scan_quad<10, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
-          CK(cudaFuncSetAttribute(k_scan_quad<14, QNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, qsmem));
-        }
-      }
-      const bool use_pdl = pdl && !p->timing;
-      int rc = SBD_OK;
-      const int use_regs = scan_regs_setting();
-      if (q1 > q0 && use_regs) {
+      constexpr int QNT = 128, B = 5;
+      if (q1 > q0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cdiv(q1 - q0, QNT));
         cfg.blockDim = dim3(QNT);
@@ -2815,25 +2293,12 @@ int launch_scan(sbd_plan* p, TrigArgs& a, bool pdl = false, int q0 = 0, int q1 =
         cfg.stream = p->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+        at[0].val.programmaticStreamSerializationAllowed = (pdl && !p->timing) ? 1 : 0;
         cfg.attrs = at;
         cfg.numAttrs = 1;
         const int* quads = p->d_quads + q0;
         int nq = q1 - q0;
-        if (use_regs == 14) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<14, QNT>, (const TrigArgs)a, quads, nq));
-        else if (use_regs == 7) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<7, QNT>, (const TrigArgs)a, quads, nq));
-        else if (use_regs == 5) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<5, QNT>, (const TrigArgs)a, quads, nq));
-        else if (use_regs == 4) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<4, QNT>, (const TrigArgs)a, quads, nq));
-        else if (use_regs == 3) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<3, QNT>, (const TrigArgs)a, quads, nq));
-        else if (use_regs == 2) CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<2, QNT>, (const TrigArgs)a, quads, nq));
-        else CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<10, QNT>, (const TrigArgs)a, quads, nq));
-        LAUNCHED();
-      } else if (q1 > q0) {
-        if (G == 5) rc = launch_scan_quad<5, QNT>(p, a, qsmem, use_pdl, q0, q1);
-        else if (G == 7) rc = launch_scan_quad<7, QNT>(p, a, qsmem, use_pdl, q0, q1);
-        else if (G == 10) rc = launch_scan_quad<10, QNT>(p, a, qsmem, use_pdl, q0, q1);
-        else rc = launch_scan_quad<14, QNT>(p, a, qsmem, use_pdl, q0, q1);
-        if (rc) return rc;
+        CK(cudaLaunchKernelEx(&cfg, k_scan_quad_regs<B, QNT>, (const TrigArgs)a, quads, nq));
         LAUNCHED();
       }
     } else {
@@ -2876,7 +2341,7 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = ((a.order == 0 || a.pipe) && !p->timing) ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = (a.order == 0 && !p->timing) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
@@ -2909,9 +2374,7 @@ int launch_win4(sbd_plan* p, TrigArgs& a)
   const int W = TX + 2 * R, Hh = TY + 2 * R;
   const int WP = W + ((17 - (W & 15)) & 15);
   const size_t smem = (size_t)WP * Hh * 8 + TX * TY + (size_t)(NT + TX * TY) * 4;
-  static int strip_min_env = -1;
-  if (strip_min_env < 0) { const char* e = getenv("SBD_STRIP_MIN"); strip_min_env = e ? atoi(e) : 0; }
-  a.strip_min = strip_min_env > 0 ? max(strip_min_env, 6) : 6;
+  a.strip_min = 6;   // swept 6 / 10 / 16 / none in round 1: 6 is best on c3s and c4
   auto kern = k_win4<VARIANT, GEN>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
@@ -2924,7 +2387,7 @@ int launch_win4(sbd_plan* p, TrigArgs& a)
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = (GEN && (a.order == 0 || a.pipe) && !p->timing) ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = (GEN && a.order == 0 && !p->timing) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
@@ -2962,7 +2425,7 @@ int launch_win8_cfg(sbd_plan* p, TrigArgs& a)
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = (GEN && (a.order == 0 || a.pipe) && !p->timing) ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = (GEN && a.order == 0 && !p->timing) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
@@ -2982,84 +2445,26 @@ int launch_win8_cfg(sbd_plan* p, TrigArgs& a)
 template <int VARIANT>
 int launch_win8(sbd_plan* p, TrigArgs& a)
 {
-  static int cfg_env = -1, min8_env = -1;
-  if (cfg_env < 0) { const char* e = getenv("SBD_WIN8_CFG"); cfg_env = e ? atoi(e) : 1; }
-  if (min8_env < 0) { const char* e = getenv("SBD_WIN8_MIN8"); min8_env = e ? atoi(e) : 0; }
-  a.strip_min = min8_env;
-  // 0: 8-cell strips where the radius allows (measured slower: 32 such strips make a chunk, a tile has only 8
-  //    chunks for its 8 warps and the longest one sets the tile's time); 1 (default): 4-cell strips, 16 chunks;
-  //    2: 4-cell strips, 512 threads
-  if (cfg_env == 0) return launch_win8_cfg<VARIANT, 256, true>(p, a);
-  if (cfg_env == 2) return launch_win8_cfg<VARIANT, 512, false>(p, a);
+  // Measured on c3 (4000 x 3000, radii to 54), window kernel alone: 4-cell strips, 256 threads (16 chunks of 32
+  // strips for the tile's 8 warps) 4.1 ms; the same with 512 threads (one chunk per warp again) 5.2 ms; 8-cell
+  // strips where the radius allows 6.2 ms -- a tile then has only 8 chunks and the longest one sets its time
+  // (sbd_plan_set_strip_cells(8) selects that form; it is the better one only for tiles of near-uniform radius).
+  a.strip_min = 0;
+  if (p->strip_cells == 8) return launch_win8_cfg<VARIANT, 256, true>(p, a);
   return launch_win8_cfg<VARIANT, 256, false>(p, a);
-}
-
-// small-radius window kernel (k_wsmall, sbd_wsmall.cuh): 32 x 8 cells per CTA, one thread per cell
-template <int VARIANT>
-int launch_wsmall(sbd_plan* p, TrigArgs& a)
-{
-  constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
-  constexpr int TX = 32, TY = 8, NT = 256;
-  const int R = a.R;
-  const size_t smem = (size_t)((TX + 2 * R) | 1) * (TY + 2 * R) * 4;
-  auto kern = k_wsmall<VARIANT, GEN>;
-  dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
-  a.nws = p->d_nws;
-  a.nwd = p->d_nwd;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(NT);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = p->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = (GEN && (a.order == 0 || a.pipe) && !p->timing) ? 1 : 0;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
-  CK(cudaLaunchKernelEx(&cfg, kern, (const TrigArgs)a)); LAUNCHED();
-  if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
-  if (GEN && a.order == 0) {
-    if (p->timing) CK(cudaEventRecord(p->ev[4], p->stream));
-    if (p->n_coastal > 0) {
-      k_final<<<cdiv(p->n_coastal, 256), 256, 0, p->stream>>>(a, p->d_idx, p->n_coastal); LAUNCHED();
-    }
-    if (p->timing) CK(cudaEventRecord(p->ev[5], p->stream));
-  }
-  CK(cudaGetLastError());
-  return SBD_OK;
 }
 
 template <int VARIANT>
 int launch_trigger(sbd_plan* p, TrigArgs& a)
 {
   // radii beyond a few cells: strip kernel (see k_win4); sbd_plan_set_window_kernel overrides
-  static int win4_min = -1;
-  if (win4_min < 0) { const char* e = getenv("SBD_WIN4_MIN"); win4_min = e ? atoi(e) : 9; }
+  constexpr int win4_min = 9;
   int mode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
-  if (mode == 4) mode = 0;   // the fused quad step is chosen in sbd_plan_step; here: the window kernel of the other paths
   // measured (profiles/r2_probe_win.txt): km-scale radii (c3, halo 54): k_win8 4.1 ms, k_win4 5.1 ms;
   // 0.1-degree radii (c4, up to 22): k_win4 0.37 ms, k_win8 0.39-0.45 ms
-  if ((mode == 5 || mode == 0) && a.R <= 8) return launch_wsmall<VARIANT>(p, a);
   if ((mode == 3 || (mode == 0 && a.R >= 32)) && a.R <= 56) return launch_win8<VARIANT>(p, a);
   if ((mode == 2 || (mode == 0 && a.R >= win4_min)) && a.R <= 56) return launch_win4<VARIANT>(p, a);
-  if (a.R <= 16) {
-    static int tile = -1;
-    if (tile < 0) { const char* e = getenv("SBD_TILE"); tile = e ? atoi(e) : 0; }
-    switch (tile) {
-      case 1: return launch_trigger_cfg<VARIANT, 64, 8, 256, 16>(p, a);
-      case 2: return launch_trigger_cfg<VARIANT, 64, 8, 128, 16>(p, a);
-      case 3: return launch_trigger_cfg<VARIANT, 32, 16, 128, 16>(p, a);
-      case 4: return launch_trigger_cfg<VARIANT, 64, 16, 512, 16>(p, a);
-      case 5: return launch_trigger_cfg<VARIANT, 64, 32, 512, 16>(p, a);
-      default: return launch_trigger_cfg<VARIANT, 64, 16, 256, 16>(p, a);
-    }
-  }
-  static int patch = -1;
-  if (patch < 0) { const char* e = getenv("SBD_PATCH"); patch = e ? atoi(e) : 1; }
-  if (patch == 0) return launch_trigger_cfg<VARIANT, 128, 64, 1024, 56, false>(p, a);
-  if (patch == 2) return launch_trigger_cfg<VARIANT, 64, 64, 512, 56, true>(p, a);
-  if (patch == 3) return launch_trigger_cfg<VARIANT, 64, 32, 256, 56, true>(p, a);
+  if (a.R <= 16) return launch_trigger_cfg<VARIANT, 64, 16, 256, 16>(p, a);
   return launch_trigger_cfg<VARIANT, 128, 64, 1024, 56, true>(p, a);
 }
 
@@ -3153,12 +2558,6 @@ int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, 
   if ((long long)(nx + 2 * h) * (ny + 2 * h) > 0x7fffffffLL) return fail(SBD_EDIMS, "plane too large for 32-bit indexing");
   int rc = ensure_device();
   if (rc) return rc;
-  if (const char* gr = getenv("SBD_L2_FETCH_GRANULARITY")) {
-    // experiment knob: the p-column gather touches short runs of cells; a 32 B fetch granule
-    // wastes less DRAM traffic than the default 64 B
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));
-    cudaGetLastError();
-  }
   sbd_plan* p = new sbd_plan();
   p->variant = variant; p->nx = nx; p->ny = ny; p->nz = nz;
   p->h = (variant == SBD_VARIANT_GENERIC) ? h : 0;
@@ -3176,7 +2575,6 @@ int sbd_plan_create(sbd_plan** out, int variant, int nx, int ny, int nz, int h, 
       cudaMalloc((void**)&p->d_cnt, 4 * sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_idx, (size_t)nx * ny * sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_quads, ((size_t)nx * ny / 4 + 1) * sizeof(int)) != cudaSuccess ||
-      cudaMalloc((void**)&p->d_quads_off, ((size_t)nx * ny / 4 + 1) * sizeof(int)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_nws, (size_t)nx * ny * sizeof(float)) != cudaSuccess ||
       cudaMalloc((void**)&p->d_nwd, (size_t)nx * ny * sizeof(float)) != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "cudaMalloc of plan planes failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -3192,12 +2590,12 @@ void sbd_plan_destroy(sbd_plan* p)
   if (!p) return;
   if (p->own_stream) cudaStreamSynchronize(p->own_stream);
   cudaFree(p->d_gzsm); cudaFree(p->d_code); cudaFree(p->d_cl); cudaFree(p->d_stats); cudaFree(p->d_carry); cudaFree(p->d_cnt);
-  cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads); cudaFree(p->d_quads_off); cudaFree(p->d_nws); cudaFree(p->d_nwd);
+  cudaFree(p->d_idx); cudaFree(p->d_cub); cudaFree(p->d_quads); cudaFree(p->d_nws); cudaFree(p->d_nwd);
   for (int i = 0; i < 6; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->e_copy) cudaEventDestroy(p->e_copy);
   if (p->e_main) cudaEventDestroy(p->e_main);
-  cudaFree(p->d_pfull); cudaFree(p->d_thc_scr[0]);
+  cudaFree(p->d_pfull);
   for (int i = 0; i < 3; ++i) cudaFree(p->d_st_in[i]);
   cudaFree(p->d_sum);
   for (auto& s : p->stage) cudaFree(s.first);
@@ -3232,6 +2630,12 @@ int sbd_plan_set_peer_sync(sbd_plan* p, uint32_t* sync_local, uint32_t* sync_up,
   if (!sync_local && (sync_up || sync_dn)) return fail(SBD_EINVAL, "neighbour flags without local flags");
   p->sync_local = sync_local; p->sync_up = sync_up; p->sync_dn = sync_dn;
   p->sync_seq = 0;
+  if (sync_local) {
+    // (re-)arming restarts the sequence at 0: stale posts of an earlier sequence in this rank's words would let every
+    // wait pass at once, so they are cleared here (collective call: every rank re-arms between two barriers)
+    CK(cudaMemsetAsync(sync_local, 0, 4 * sizeof(uint32_t), p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+  }
   return SBD_OK;
 }
 int sbd_plan_set_row_window(sbd_plan* p, int row_lo, int row_hi)
@@ -3243,28 +2647,27 @@ int sbd_plan_set_row_window(sbd_plan* p, int row_lo, int row_hi)
 }
 int sbd_set_window_kernel_default(int mode)
 {
-  if (mode < 0 || mode > 5) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 k_win4, 3 k_win8, 4 fused quad step, 5 k_wsmall");
+  if (mode < 0 || mode > 3) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile kernel, 2 k_win4, 3 k_win8");
   g_window_kernel_default = mode;
   return SBD_OK;
 }
 int sbd_plan_set_window_kernel(sbd_plan* p, int mode)
 {
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
-  if (mode < 0 || mode > 5) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile, 2 k_win4, 3 k_win8, 4 fused quad step, 5 k_wsmall");
+  if (mode < 0 || mode > 3) return fail(SBD_EINVAL, "window kernel: 0 auto, 1 tile kernel, 2 k_win4, 3 k_win8");
   p->window_kernel = mode;
   return SBD_OK;
 }
-int sbd_plan_set_pipelined(sbd_plan* p, int on)
+int sbd_plan_set_strip_cells(sbd_plan* p, int cells)
 {
-  if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
-  if (on && !p->d_thc_scr[0]) {
-    const size_t n2 = (size_t)p->nx * p->ny;
-    CK(cudaMalloc((void**)&p->d_thc_scr[0], 2 * n2 * sizeof(float) + 16));
-    p->d_thc_scr[1] = p->d_thc_scr[0] + n2;
-    p->d_pipe_ctr = reinterpret_cast<unsigned*>(p->d_thc_scr[0] + 2 * n2);
-    CK(cudaMemset(p->d_pipe_ctr, 0, 16));
-  }
-  p->pipelined = on != 0;
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  if (cells != 4 && cells != 8) return fail(SBD_EINVAL, "strip cells: 4 or 8");
+  p->strip_cells = cells;
+  return SBD_OK;
+}
+int sbd_set_stats_mode(int sequential)
+{
+  g_stats_seq.store(sequential ? 1 : 0);
   return SBD_OK;
 }
 int sbd_plan_set_timing(sbd_plan* p, int on)
@@ -3281,7 +2684,7 @@ int sbd_plan_last_timing(sbd_plan* p, float* ms3)
   ms3[0] = ms3[1] = ms3[2] = 0.0f;
   CK(cudaStreamSynchronize(p->stream));
   CK(cudaEventElapsedTime(&ms3[0], p->ev[0], p->ev[1]));              // window kernel (or the fused step kernel)
-  if (p->variant == SBD_VARIANT_GENERIC && p->last_order != 2) {   // (last_order 3: the one-kernel step sits in the scan slot)
+  if (p->variant == SBD_VARIANT_GENERIC && p->last_order != 2) {
     CK(cudaEventElapsedTime(&ms3[1], p->ev[2], p->ev[3]));            // level-scan kernel
     if (p->last_order == 0) CK(cudaEventElapsedTime(&ms3[2], p->ev[4], p->ev[5]));  // threshold kernel
   }
@@ -3294,11 +2697,26 @@ int sbd_plan_use_own_stream(sbd_plan* p)
   return SBD_OK;
 }
 void* sbd_plan_get_stream(sbd_plan* p) { return p ? (void*)p->stream : nullptr; }
+// a window kernel that gave up waiting for a neighbour's post left a marker in sync_local[2], [3]: its sums used
+// neighbour rows that may not have been in place, so the step's results are not to be trusted
+static int check_peer_timeout(sbd_plan* p)
+{
+  if (!p->sync_local) return SBD_OK;
+  uint32_t mark[2] = {0u, 0u};
+  CK(cudaMemcpy(mark, p->sync_local + 2, sizeof mark, cudaMemcpyDeviceToHost));
+  if (mark[0] || mark[1]) {
+    snprintf(g_err, sizeof g_err, "neighbour rank did not post its theta plane within 4 s (north: step %u, south: step %u); "
+             "results of that step are invalid", mark[0], mark[1]);
+    return SBD_EPEER;
+  }
+  return SBD_OK;
+}
+
 int sbd_plan_sync(sbd_plan* p)
 {
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
   CK(cudaStreamSynchronize(p->stream));
-  return SBD_OK;
+  return check_peer_timeout(p);
 }
 
 // static plane 1: sigmoid statistics (sequential-order exact) + gzsm = (gmma*z)*sigmoid(sigma)
@@ -3376,25 +2794,6 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
       }
       CK(cub::DeviceSelect::If(p->d_cub, need2, it, p->d_quads, p->d_cnt + 3, n2 / 4, qf, st));
       LAUNCHED();
-      // the complement: quads without any coastal-zone cell (static; filled with the missing value every step)
-      QuadOffFlag qo{qf};
-      size_t need3 = 0;
-      CK(cub::DeviceSelect::If(nullptr, need3, it, p->d_quads_off, p->d_cnt + 2, n2 / 4, qo, st));
-      if (need3 > p->cub_bytes) {
-        CK(cudaStreamSynchronize(st));
-        CK(cudaFree(p->d_cub));
-        p->d_cub = nullptr;
-        CK(cudaMalloc(&p->d_cub, need3));
-        p->cub_bytes = need3;
-      }
-      int n_act = 0;
-      CK(cudaMemcpyAsync(&n_act, p->d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));   // keep the cell count
-      CK(cudaStreamSynchronize(st));
-      CK(cub::DeviceSelect::If(p->d_cub, need3, it, p->d_quads_off, p->d_cnt + 2, n2 / 4, qo, st));
-      LAUNCHED();
-      CK(cudaMemcpyAsync(&p->n_quads_off, p->d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      CK(cudaMemcpyAsync(p->d_cnt + 2, &n_act, sizeof(int), cudaMemcpyHostToDevice, st));
     }
   }
   int cnt[4];
@@ -3406,11 +2805,10 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
   if (p->variant == SBD_VARIANT_GENERIC && cnt[2] != cnt[1])
     return fail(SBD_ECUDA, "internal: compaction count differs from the coastal-cell count");
   p->R = (p->nn_max <= 16) ? p->nn_max : min(p->nn_max, 56);  // see launch_trigger
-  // split row of the hybrid host path (SBD_E2E_SPLIT = fraction of rows that travel by DMA)
+  // split row of the hybrid host path
   p->ysplit = 0; p->n_quads_top = 0;
   if (p->variant == SBD_VARIANT_GENERIC && p->n_quads > 0) {
-    static float frac = -1.0f;
-    if (frac < 0.0f) { const char* e = getenv("SBD_E2E_SPLIT"); frac = e ? (float)atof(e) : 0.9f; if (frac > 1.0f) frac = 1.0f; }
+    constexpr float frac = 0.9f;   // share of the rows that travels by DMA (swept 0.5 .. 1.0 in round 1)
     p->ysplit = (int)(frac * p->ny);
     if (p->ysplit > 0) {
       std::vector<int> hq(p->n_quads);
@@ -3552,13 +2950,6 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
   if (!p || p->variant != SBD_VARIANT_GENERIC) return fail(SBD_EINVAL, "generic plan required");
   if (!p->have_static) return fail(SBD_EINVAL, "sbd_plan_set_static has not been called");
   if (!pp || !u || !v || !theta || !ws || !wd || !thc || !sb) return fail(SBD_EINVAL, "NULL argument");
-  static int order_env = -1;
-  if (order_env < 0) { const char* e = getenv("SBD_ORDER"); order_env = e ? atoi(e) : 1; }
-  if (order_env == 0) {
-    int rc = sbd_plan_step_scan(p, pp, u, v);
-    if (rc) return rc;
-    return sbd_plan_step_finish(p, timestep, step, theta, ws, wd, thc, sb, flags);
-  }
   // single call, nothing to overlap with on the host side: window kernel first, the level scan as
   // its programmatic dependent with the thresholds in its epilogue (two launches, no scratch pass)
   const size_t n2 = (size_t)p->nx * p->ny, n3 = n2 * p->nz, nh = plane_elems(p);
@@ -3593,69 +2984,7 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
     if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
     return flush_out(p, pend, any_host);
   }
-  // Small search radii (N512-class grids): the whole step is ONE kernel -- every level-scan thread also sums
-  // the windows of its four cells (sbd_stepq.cuh).  sbd_plan_set_window_kernel(1..3) keeps the two-kernel forms.
-  const int wmode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
-  const bool p_map = !is_device_ptr(pp) && a.p != nullptr && mapped_host_ptr(pp) == a.p;
-  if (wmode == 4 && stepq_ok(p, a) && !p->pipelined) {   // measured slower than the two-kernel step: opt-in only
-    a.order = 1; p->last_order = 3;
-    if (p_map && p->n_quads_top > 0 && !p->timing) {
-      // hybrid transfer for pinned host p (see below): southern quads gather in place, northern rows by DMA
-      if (!p->copy_stream) {
-        CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&p->e_copy, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&p->e_main, cudaEventDisableTiming));
-        CK(cudaMalloc((void**)&p->d_pfull, n3 * sizeof(float)));
-      }
-      CK(cudaEventRecord(p->e_main, p->stream));
-      CK(cudaStreamWaitEvent(p->copy_stream, p->e_main, 0));
-      CK(cudaMemcpy2DAsync(p->d_pfull + (size_t)p->yfirst * p->nx, n2 * sizeof(float),
-                           pp + (size_t)p->yfirst * p->nx, n2 * sizeof(float),
-                           (size_t)(p->ysplit - p->yfirst) * p->nx * sizeof(float), p->nz, cudaMemcpyHostToDevice,
-                           p->copy_stream));
-      CK(cudaEventRecord(p->e_copy, p->copy_stream));
-      if ((rc = launch_stepq(p, a, p->n_quads_top, p->n_quads, true))) return rc;
-      CK(cudaStreamWaitEvent(p->stream, p->e_copy, 0));
-      TrigArgs b = a;
-      b.p = p->d_pfull;
-      b.sync_local = nullptr;   // the handshake ran in the first launch
-      if ((rc = launch_stepq(p, b, 0, p->n_quads_top, false))) return rc;
-      return flush_out(p, pend, any_host);
-    }
-    if ((rc = launch_stepq(p, a, 0, p->n_quads, true))) return rc;
-    return flush_out(p, pend, any_host);
-  }
   a.order = 1; p->last_order = 1;
-  // Pipelined steps (device-resident inputs only): see TrigArgs::pipe
-  if (p->pipelined && !any_host && pend.empty() && !p->timing && scan_uses_regs()) {
-    a.pipe = 1;
-    a.thc_scr = p->d_thc_scr[p->pipe_seq++ & 1u];
-    a.pipe_ctr = p->d_pipe_ctr;
-  }
-  // Optional (SBD_FUSED=1): one fused, warp-specialised launch.  Measured on c2: 61.9 us per step
-  // against 51 us for the two-kernel path below -- a CTA holds its window warps' registers until
-  // its scan warps are done, which leaves only 12 streaming warps per SM -- so it is off by default.
-  {
-    static int fused_env = -1;
-    if (fused_env < 0) { const char* e = getenv("SBD_FUSED"); fused_env = e ? atoi(e) : 0; }
-    if (fused_env && a.R <= 16 && (p->nx % 4) == 0 && is_device_ptr(pp)) {
-      constexpr int TX = 64, TY = 16, G = 10;
-      const int R = a.R;
-      const size_t cells = (size_t)(TX + 2 * R) * (TY + 2 * R);
-      const size_t smem = (size_t)2 * G * 128 * 16 + (size_t)TX * TY * 4 * 4 + cells * 4 +
-                          ((size_t)(TY + 2 * R) * ((TX + 2 * R + 31) / 32) + 2) * 4;
-      auto kern = k_step_fused<TX, TY, 16, G>;
-      static bool attr = false;
-      if (!attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-      dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
-      p->last_order = 2;
-      if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
-      kern<<<grid, 384, smem, p->stream>>>(a); LAUNCHED();
-      if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
-      CK(cudaGetLastError());
-      return flush_out(p, pend, any_host);
-    }
-  }
   // Hybrid transfer for pinned host p: while the scan of the southern quads gathers its pressure
   // columns over PCIe in place (zero-copy), the DMA engine copies the northern rows of every
   // level into device memory; the northern quads are scanned from HBM afterwards.  Both halves

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (SPLIT && a.order == 1 && !a.pipe) asm volatile("griddepcontrol.launch_dependents;");
+  if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
 
   if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {  // multi-GPU post / wait, as in k_trigger
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
@@ -533,17 +533,6 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
         const int nn = (int)(a.code[own_index<VARIANT>(a.g, gx, gy)] & 0x7fffu);
         window_sums_global<VARIANT>(a, gx, gy, nn, T_l, T_s, c_l, c_s);
         finish_cell<VARIANT, SPLIT>(a, gx, gy, (b & 0x80u) != 0, T_l, T_s, c_l, c_s, s_lev);
-      }
-    }
-  }
-
-  if (SPLIT && a.pipe) {  // pipelined steps: see the end of k_trigger
-    if (tid == 0) {
-      const unsigned n_cta = gridDim.x * gridDim.y;
-      if (atomicAdd(a.pipe_ctr, 1u) == n_cta - 1u) {
-        *a.pipe_ctr = 0u;
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        asm volatile("griddepcontrol.launch_dependents;");
       }
     }
   }

@@ -154,10 +154,9 @@ class Plan:
         _capi.check(self.lib.sbd_plan_set_peer_sync(self._h, q(sync_local), q(sync_up), q(sync_dn)),
                     "plan_set_peer_sync")
 
-    def set_pipelined(self, on=True):
-        """Overlap consecutive device-resident steps (inputs of a step must be complete before the
-        previous step call is issued).  See sbd_plan_set_pipelined."""
-        _capi.check(self.lib.sbd_plan_set_pipelined(self._h, 1 if on else 0), "plan_set_pipelined")
+    def set_strip_cells(self, cells):
+        """Cells per strip of the k_win8 window kernel: 4 (default) or 8.  See sbd_plan_set_strip_cells."""
+        _capi.check(self.lib.sbd_plan_set_strip_cells(self._h, int(cells)), "plan_set_strip_cells")
 
     def window_info(self):
         """(nn, n_land, n_sea): int32 (ny, nx) arrays -- the radius at which the growing-window loop
@@ -171,7 +170,7 @@ class Plan:
         _capi.check(self.lib.sbd_plan_set_row_window(self._h, int(row_lo), int(row_hi)), "plan_set_row_window")
 
     def set_window_kernel(self, mode):
-        """0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4).  See sbd_plan_set_window_kernel."""
+        """0 auto, 1 tile kernel (k_trigger), 2 k_win4, 3 k_win8.  See sbd_plan_set_window_kernel."""
         _capi.check(self.lib.sbd_plan_set_window_kernel(self._h, int(mode)), "plan_set_window_kernel")
 
     def use_own_stream(self):

@@ -101,8 +101,8 @@ def test_exact_parallel_stats_adversarial(oracle):
 @pytest.mark.parametrize("name,wk", [("t_py", 0), ("c5", 0), ("t_py", 2), ("c5", 2), ("t_py", 3), ("c5", 3),
                                      ("t_py", 1), ("c5", 1)])
 def test_py_diag_time_loop(oracle, name, wk):
-    """wk = 0: automatic = the small-radius kernel k_wsmall on these grids; 1: the tile kernel k_trigger;
-    2 / 3 force the strip window kernels (k_win4 / k_win8)."""
+    """wk = 0 / 1: the tile kernel k_trigger (the automatic choice on these grids); 2 / 3 force the strip window
+    kernels (k_win4 / k_win8)."""
     with window_kernel(wk):
         _py_diag_time_loop(oracle, name)
 
@@ -285,12 +285,10 @@ def test_generic_edges_dist(oracle, name):
 
 @pytest.mark.parametrize("name,level_scan,wk", [("t_gen", 0, 0), ("t_gen", 1, 0), ("c1", 0, 0), ("t_gen", 0, 2),
                                                  ("t_gen", 1, 2), ("c1", 0, 2), ("t_gen", 0, 3), ("t_gen", 1, 3),
-                                                 ("c1", 0, 3), ("t_gen", 0, 1), ("c1", 0, 1), ("t_gen", 0, 4),
-                                                 ("c1", 0, 4)])
+                                                 ("c1", 0, 3), ("t_gen", 0, 1), ("c1", 0, 1)])
 def test_generic_seabreeze_diag_steps(oracle, name, level_scan, wk):
-    """wk = 0: automatic = k_wsmall + level scan on these small-radius grids; 1: the tile window kernel (k_trigger);
-    2 / 3: the strip window kernels (k_win4 / k_win8) forced; 4: the one-kernel step (k_step_quad; opt-in, it
-    applies to the minloc level search only)."""
+    """wk = 0 / 1: the tile window kernel (k_trigger, the automatic choice on these small-radius grids);
+    2 / 3: the strip window kernels (k_win4 / k_win8) forced."""
     with window_kernel(wk):
         _generic_seabreeze_diag_steps(oracle, name, level_scan)
 
@@ -378,45 +376,6 @@ def test_generic_split_api_matches_single_call(oracle):
         for a, b, c, nm in zip(so, st[0], st[1], ("windspeed", "winddir", "thc", "sb_con")):
             assert_bits_equal(a, b.cpu().numpy(), "single %s step %d" % (nm, step))
             assert_bits_equal(a, c.cpu().numpy(), "split %s step %d" % (nm, step))
-
-
-@pytest.mark.parametrize("name", ["t_gen", "c1"])
-def test_generic_pipelined_steps(oracle, name):
-    """sbd_plan_set_pipelined: the window kernel of step k+1 runs under the level scan of step k
-    (n_thc through a double-buffered scratch plane).  12 steps enqueued back to back on preloaded
-    inputs, no host synchronisation in between: every step's sb_con / flags and the final state
-    equal the oracle's bits."""
-    import torch
-    cfg = synth.CONFIGS[name]
-    case = generic_case(cfg, oracle)
-    ny, nx = cfg.ny, cfg.nx
-    dev = torch.device("cuda:0")
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    steps = list(range(1, 13)) + [15, 16]
-    so = [np.zeros((ny, nx), np.float32) for _ in range(4)]
-    ref_sb, ref_fl, dins = [], [], []
-    for step in steps:
-        theta_h, p, u, v = generic_step_inputs(cfg, case, step, oracle)
-        fo = oracle.seabreeze_diag(cfg.timestep, step, p, u, v, theta_h, case["mask_h"], case["z_h"], case["sigma_h"], *so, cfg.h)
-        ref_sb.append(so[3].copy()); ref_fl.append(np.array(fo).copy())
-        dins.append((t(p), t(u), t(v), t(theta_h)))
-    plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
-    plan.set_static(t(case["mask_h"]), t(case["z_h"]), t(case["sigma_h"]))
-    plan.set_pipelined(True)
-    st = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(3)]
-    sbs = [torch.full((ny, nx), -7.0, dtype=torch.float32, device=dev) for _ in steps]
-    fls = [torch.full((ny, nx), 9, dtype=torch.uint8, device=dev) for _ in steps]
-    torch.cuda.synchronize()
-    for i, step in enumerate(steps):
-        dp, du, dv, dth = dins[i]
-        plan.step(cfg.timestep, step, dp, du, dv, dth, *st, sbs[i], flags=fls[i])
-    plan.sync()
-    for i, step in enumerate(steps):
-        assert_bits_equal(ref_sb[i], sbs[i].cpu().numpy(), "sb_con step %d" % step)
-        assert np.array_equal(ref_fl[i], fls[i].cpu().numpy()), "flags step %d" % step
-    for a, b, nm in zip(so[:3], st, ("windspeed", "winddir", "thc")):
-        assert_bits_equal(a, b.cpu().numpy(), "final " + nm)
-    plan.close()
 
 
 @pytest.mark.parametrize("name", ["t_gen", "c1"])
@@ -523,7 +482,7 @@ def test_generic_device_pointers_torch(oracle):
     plan.close()
 
 
-@pytest.mark.parametrize("wk", [0, 1, 2])
+@pytest.mark.parametrize("wk", [0, 1, 2, 3, 38])
 @pytest.mark.parametrize("nx,ny,h,filt,expect", [(160, 96, 24, 14.0, "big tile"), (320, 240, 54, 40.0, "big tile"),
                                                    (300, 200, 72, 60.0, "global path")])
 def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
@@ -534,7 +493,11 @@ def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
     cfg = synth.Config("t_big", nx, ny, 4, h, "generic", filt, True, 1440.0, "wide-window test")
     case = generic_case(cfg, oracle)
     plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, cfg.h)
-    plan.set_window_kernel(wk)
+    if wk == 38:     # k_win8 with 8-cell strips
+        plan.set_window_kernel(3)
+        plan.set_strip_cells(8)
+    else:
+        plan.set_window_kernel(wk)
     plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
     nn_max = plan.info()["nn_max"]
     assert nn_max > 16, plan.info()
@@ -586,43 +549,6 @@ def test_wide_windows_signed_class_fallback(oracle, what):
             assert_bits_equal(a, b, "%s %s step %d" % (what, nm, step))
         assert np.array_equal(fo, fp)
     plan.close()
-
-
-def test_fused_step_kernel_variant():
-    """SBD_FUSED=1 selects the single fused (warp-specialised) step kernel; same bits as the default
-    two-kernel path.  The switch is read once per process, hence the subprocess."""
-    import os
-    import subprocess
-    import sys
-    code = r'''
-import sys, numpy as np, torch
-sys.path[:0] = [%r, %r]
-from oracle import oracle as O
-from seabreeze_param_b200 import generic, synth
-from util import generic_case, generic_step_inputs
-O.set_math(1)
-cfg = synth.Config("t_f", 192, 80, 9, 6, "generic", 5.0, False, 1440.0, "fused test")
-case = generic_case(cfg, O)
-dev = torch.device("cuda:0")
-t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-plan = generic.Plan(0, cfg.nx, cfg.ny, cfg.nz, cfg.h)
-plan.set_static(t(case["mask_h"]), t(case["z_h"]), t(case["sigma_h"]))
-so = [np.zeros((cfg.ny, cfg.nx), np.float32) for _ in range(4)]
-sg = [torch.zeros((cfg.ny, cfg.nx), dtype=torch.float32, device=dev) for _ in range(4)]
-fg = torch.zeros((cfg.ny, cfg.nx), dtype=torch.uint8, device=dev)
-for step in (1, 2, 15):
-    th, p, u, v = generic_step_inputs(cfg, case, step, O)
-    fo = O.seabreeze_diag(cfg.timestep, step, p, u, v, th, case["mask_h"], case["z_h"], case["sigma_h"], *so, cfg.h)
-    plan.step(cfg.timestep, step, t(p), t(u), t(v), t(th), *sg, flags=fg)
-    plan.sync()
-    for a, b in zip(so, sg):
-        b = b.cpu().numpy()
-        assert ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all()
-    assert np.array_equal(fo, fg.cpu().numpy())
-print("FUSED_OK")
-''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, SBD_FUSED="1"))
-    assert r.returncode == 0 and "FUSED_OK" in r.stdout, r.stdout + r.stderr
 
 
 def test_determinism_run_twice(oracle):

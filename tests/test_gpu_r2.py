@@ -224,3 +224,22 @@ def test_one_shot_plan_cache_and_host_registration(oracle):
     assert m1.value - m0.value == 2
     assert p.nbytes >= (1 << 20) and p.ctypes.data in _capi._REGISTERED    # 18.9 MB p was page-locked
     lib.sbd_plan_cache_clear()
+
+
+def test_sequential_statistics_cross_check():
+    """sbd_set_stats_mode(1): the plain one-warp sequential chain (k_stats_seq) instead of the exact parallel
+    formulation (k_stats_exact) -- the same bits, on a field with ties, zeros and binade crossings."""
+    from seabreeze_param_b200 import _capi
+    lib = _capi.load()
+    rng = np.random.default_rng(3)
+    a = (rng.random((300, 517)) * 300 * (rng.random((300, 517)) > 0.6)).astype(np.float32)
+    a[7, :40] = 2.5
+    st_p = np.zeros(4, np.float32); st_s = np.zeros(4, np.float32)
+    sm_p = generic.sigmoid(a, stats=st_p)
+    lib.sbd_set_stats_mode(1)
+    try:
+        sm_s = generic.sigmoid(a, stats=st_s)
+    finally:
+        lib.sbd_set_stats_mode(0)
+    assert_bits_equal(st_p, st_s, "statistics")
+    assert_bits_equal(sm_p, sm_s, "sigmoid")

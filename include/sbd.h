@@ -153,6 +153,36 @@ int sbd_swap_bounds_ew_f32(float* field, int nx, int ny, int h);
 int sbd_swap_bounds_dev_f32(float* d_field, int nx, int ny, int h, int ns_mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * UM hook (UM/vn10.7/sea_breeze_diag.F90 = U): the UM's own dummy lists (fortran/sea_breeze_diag_um.F90).
+ * Planes are row_length x rows interiors with the halo widths of atm_fields_bounds_mod:
+ *   tdims_s (halo_s on every side): theta, z, sigma (U:78-117);   tdims_l (halo_i x halo_j): mask / coast /
+ *   landfrac (U:339-341, U:471-476);   pdims / tdims (no halo): p, u, v, windspeed, winddir, thc, sb_con.
+ * Return value = the routine's `error` (U:102, U:198-201: 1 for rows < 1 or levels < 1).
+ * ------------------------------------------------------------------------------------------- */
+
+/* seabreeze_diag(timestep, timestep_number, p, u, v, theta, z, sigma, mask, windspeed, winddir, thc, sb_con, error)
+ * U:55-326.  mask (signed coast distance) has halo_l, theta / z / sigma halo_s; the growing window (U:234-258) may
+ * reach min(halo_s, halo_l) cells.  Level search: U's early-exit scan (U:265-274) unless prm says otherwise.
+ * theta_to_t0 != 0 reproduces the side effect of U:210-211: theta (the whole halo'd array) is overwritten by
+ * t0 = theta - gmma z sigmoid(sigma). */
+int sbd_um_seabreeze_diag_f32(float timestep, int timestep_number, const float* p, const float* u, const float* v,
+                              float* theta, const float* z, const float* sigma, const float* mask, float* windspeed,
+                              float* winddir, float* thc, float* sb_con, int row_length, int rows, int levels,
+                              int halo_s, int halo_l, int theta_to_t0, const sbd_params* prm, uint8_t* flags);
+/* get_edges(mask, icefrac, landfrac)  U:328-446.  mask: tdims_l (out: coast flag + swapped halos). */
+int sbd_um_get_edges_f32(float* mask, const float* icefrac, const float* landfrac, int row_length, int rows,
+                         int halo_i, int halo_j);
+/* get_dist(landfrac, coast)  U:448-601.  landfrac, coast: tdims_l (coast in: flag, out: signed distance + swapped
+ * halos); true_latitude / true_longitude: row_length x rows, degrees (trignometric_mod, U:461); search radius
+ * halo_i x halo_j cells (U:515-516); maxdist = 180 in U (module parameter). */
+int sbd_um_get_dist_f32(const float* landfrac, float* coast, const float* true_latitude, const float* true_longitude,
+                        int row_length, int rows, int halo_i, int halo_j, float maxdist);
+/* swap_bounds(field, row_len, rows, levels, halo_i, halo_j, fld_type, l_vector)  U:408-410 (halo_exchange module of
+ * the UM), single domain: east-west periodic, north-south edge rows.  fld_type / l_vector do not matter for scalars
+ * on one domain; between GPUs see seabreeze_param_b200/halo.py. */
+int sbd_um_swap_bounds_f32(float* field, int row_len, int rows, int levels, int halo_i, int halo_j);
+
+/* ---------------------------------------------------------------------------------------------
  * Python (f2py module `seabreeze`) entry points: same positional meaning as the f2py signatures.
  * ------------------------------------------------------------------------------------------- */
 

@@ -42,6 +42,8 @@ def lib():
         L.orc_sobel.argtypes = [fp, i, i, i, fp, fp]
         L.orc_window_info.argtypes = [fp, i, i, i, f, vp, vp, vp]
         L.orc_seabreeze_diag.argtypes = [f, i] + [fp] * 11 + [i, i, i, i, i, i, vp]
+        L.orc_um_swap_bounds.argtypes = [fp, i, i, i, i]
+        L.orc_um_get_dist.argtypes = [fp, fp, fp, fp, i, i, i, i, f]
         _lib = L
     return _lib
 
@@ -185,3 +187,22 @@ def seabreeze_diag(timestep, step, p, u, v, theta, mask, z, sigma, ws, wd, thc, 
     if rc:
         raise RuntimeError("orc_seabreeze_diag status %d" % rc)
     return fl
+
+
+def um_swap_bounds(field, nx, ny, hi, hj):
+    assert field.dtype == np.float32 and field.flags.c_contiguous and field.shape == (ny + 2 * hj, nx + 2 * hi)
+    lib().orc_um_swap_bounds(_p(field), nx, ny, hi, hj)
+    return field
+
+
+def um_get_dist(landfrac, coast_l, lat2d, lon2d, hi, hj, maxdist=180.0):
+    """UM get_dist(landfrac, coast) (UM/vn10.7/sea_breeze_diag.F90:448-601), literal scatter; returns the new halo'd
+    coast array (signed distance)."""
+    land, lat2d, lon2d = _c(landfrac), _c(lat2d), _c(lon2d)
+    ny, nx = land.shape
+    out = _c(coast_l).copy()
+    assert out.shape == (ny + 2 * hj, nx + 2 * hi)
+    rc = lib().orc_um_get_dist(_p(land), _p(out), _p(lat2d), _p(lon2d), nx, ny, hi, hj, float(maxdist))
+    if rc:
+        raise RuntimeError("orc_um_get_dist status %d" % rc)
+    return out

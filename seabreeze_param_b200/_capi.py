@@ -25,6 +25,7 @@ SYMBOLS = [
     "sbd_plan_set_peer_sync", "sbd_plan_set_strip_cells", "sbd_set_stats_mode", "sbd_plan_set_window_kernel", "sbd_set_window_kernel_default", "sbd_plan_set_row_window", "sbd_get_edges_ex_f32", "sbd_plan_window_info",
     "sbd_get_edges_f64", "sbd_get_dist_f64", "sbd_sigmoid_f64", "sbd_seabreeze_diag_f64", "sbd_swap_bounds_f64",
     "sbd_plan_cache_clear", "sbd_plan_cache_stats", "sbd_host_register", "sbd_host_unregister",
+    "sbd_um_seabreeze_diag_f32", "sbd_um_get_edges_f32", "sbd_um_get_dist_f32", "sbd_um_swap_bounds_f32",
 ]
 
 
@@ -119,6 +120,10 @@ def load():
     lib.sbd_plan_cache_stats.argtypes = [ip, ip, ip]
     lib.sbd_host_register.argtypes = [vp, C.c_size_t]
     lib.sbd_host_unregister.argtypes = [vp]
+    lib.sbd_um_seabreeze_diag_f32.argtypes = [f, i] + [fp] * 11 + [i, i, i, i, i, i, C.POINTER(SbdParams), vp]
+    lib.sbd_um_get_edges_f32.argtypes = [fp, fp, fp, i, i, i, i]
+    lib.sbd_um_get_dist_f32.argtypes = [fp, fp, fp, fp, i, i, i, i, f]
+    lib.sbd_um_swap_bounds_f32.argtypes = [fp, i, i, i, i, i]
     _LIB = lib
     return lib
 

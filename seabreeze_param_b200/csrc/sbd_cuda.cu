@@ -2064,6 +2064,8 @@ __global__ void k_widen(const float* __restrict__ src, double* __restrict__ dst,
   if (i < n) dst[i] = (double)src[i];
 }
 
+#include "sbd_um.cuh"
+
 }  // namespace sbdk
 using namespace sbdk;
 
@@ -3648,6 +3650,147 @@ int sbd_seabreeze_diag_f64(double timestep, int step, const double* pp, const do
   CK(cudaStreamSynchronize(t.st));
   if ((rc = sbd_seabreeze_diag_f32((float)timestep, step, d_p, d_u, d_v, d_th, d_mk, d_z, d_sg, d_ws, d_wd, d_thc,
                                    d_sb, nx, ny, nz, h, prm, flags))) return rc;
+  return t.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// UM hook (UM/vn10.7/sea_breeze_diag.F90): the same arithmetic behind the UM's own dummy lists -- two halo widths,
+// `error`, theta overwritten by t0, 2-D latitude / longitude, the 8-argument swap_bounds.  See include/sbd.h.
+// ---------------------------------------------------------------------------------------------
+static int um_halo_fill(cudaStream_t st, float* d_f, int nx, int ny, int hi, int hj, int levels)
+{
+  const long long per = 2LL * hj * (nx + 2 * hi) + 2LL * hi * ny;
+  const long long tot = per * levels;
+  if (tot > 0) { k_um_halo<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_f, nx, ny, hi, hj, levels); LAUNCHED(); }
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+
+int sbd_um_swap_bounds_f32(float* field, int row_len, int rows, int levels, int halo_i, int halo_j)
+{
+  if (!field) return fail(SBD_EINVAL, "NULL argument");
+  if (row_len < 1 || rows < 1 || levels < 1) return fail(SBD_EDIMS, "bad dims");
+  if (halo_i < 0 || halo_j < 0) return fail(SBD_EINVAL, "negative halo");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  void* d;
+  const size_t n = (size_t)(row_len + 2 * halo_i) * (rows + 2 * halo_j) * levels;
+  if ((rc = t.out(field, n * 4, true, &d))) return rc;
+  if ((rc = um_halo_fill(t.st, (float*)d, row_len, rows, halo_i, halo_j, levels))) return rc;
+  return t.finish();
+}
+
+int sbd_um_get_edges_f32(float* mask, const float* icefrac, const float* landfrac, int nx, int ny, int halo_i, int halo_j)
+{
+  if (!mask || !icefrac || !landfrac) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  if (halo_i < 1 || halo_j < 1) return fail(SBD_EINVAL, "halo must be >= 1");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  const size_t n2 = (size_t)nx * ny, nl = (size_t)(nx + 2 * halo_i) * (ny + 2 * halo_j);
+  const float *d_ice, *d_land;
+  void *d_mask, *d_coast;
+  if ((rc = t.in(icefrac, n2, &d_ice))) return rc;
+  if ((rc = t.in(landfrac, n2, &d_land))) return rc;
+  if ((rc = t.out(mask, nl * 4, true, &d_mask))) return rc;
+  if ((rc = t.scratch(n2 * 4, &d_coast))) return rc;
+  dim3 g(cdiv(nx, 128), ny);
+  k_um_binarise<<<g, 128, 0, t.st>>>((float*)d_mask, d_ice, d_land, nx, ny, halo_i, halo_j); LAUNCHED();
+  if ((rc = um_halo_fill(t.st, (float*)d_mask, nx, ny, halo_i, halo_j, 1))) return rc;          // U:408
+  k_um_sobel<<<g, 128, 0, t.st>>>((const float*)d_mask, (float*)d_coast, nx, ny, halo_i, halo_j); LAUNCHED();
+  k_um_embed<<<g, 128, 0, t.st>>>((float*)d_mask, (const float*)d_coast, nx, ny, halo_i, halo_j); LAUNCHED();   // U:438
+  if ((rc = um_halo_fill(t.st, (float*)d_mask, nx, ny, halo_i, halo_j, 1))) return rc;          // U:440
+  CK(cudaGetLastError());
+  return t.finish();
+}
+
+int sbd_um_get_dist_f32(const float* landfrac_l, float* coast_l, const float* true_latitude, const float* true_longitude,
+                        int nx, int ny, int halo_i, int halo_j, float maxdist)
+{
+  if (!landfrac_l || !coast_l || !true_latitude || !true_longitude) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  if (halo_i < 0 || halo_j < 0) return fail(SBD_EINVAL, "negative halo");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp t;
+  const size_t n2 = (size_t)nx * ny, nl = (size_t)(nx + 2 * halo_i) * (ny + 2 * halo_j);
+  const float *d_land_l, *d_lat, *d_lon;
+  void *d_coast_l, *d_land, *d_coast, *d_bits;
+  if ((rc = t.in(landfrac_l, nl, &d_land_l))) return rc;
+  if ((rc = t.in(true_latitude, n2, &d_lat))) return rc;
+  if ((rc = t.in(true_longitude, n2, &d_lon))) return rc;
+  if ((rc = t.out(coast_l, nl * 4, true, &d_coast_l))) return rc;
+  const int wpr = cdiv(nx, 32);
+  if ((rc = t.scratch(n2 * 4, &d_land))) return rc;
+  if ((rc = t.scratch(n2 * 4, &d_coast))) return rc;
+  if ((rc = t.scratch((size_t)ny * wpr * 4, &d_bits))) return rc;
+  dim3 g(cdiv(nx, 128), ny);
+  k_um_extract<<<g, 128, 0, t.st>>>((float*)d_land, d_land_l, nx, ny, halo_i, halo_j); LAUNCHED();             // U:521
+  k_um_extract<<<g, 128, 0, t.st>>>((float*)d_coast, (const float*)d_coast_l, nx, ny, halo_i, halo_j); LAUNCHED();
+  k_coast_bits<<<g, 128, 0, t.st>>>((const float*)d_coast, nx, ny, nx, 0, (uint32_t*)d_bits, wpr); LAUNCHED();
+  k_um_dist<<<g, 128, 0, t.st>>>((const uint32_t*)d_bits, wpr, (const float*)d_land, d_lat, d_lon, nx, ny, halo_i, halo_j,
+                                 maxdist, (float*)d_coast_l, halo_i, halo_j); LAUNCHED();
+  if ((rc = um_halo_fill(t.st, (float*)d_coast_l, nx, ny, halo_i, halo_j, 1))) return rc;                    // U:598
+  CK(cudaGetLastError());
+  return t.finish();
+}
+
+int sbd_um_seabreeze_diag_f32(float timestep, int timestep_number, const float* pp, const float* u, const float* v,
+                              float* theta, const float* z, const float* sigma, const float* mask, float* windspeed,
+                              float* winddir, float* thc, float* sb_con, int nx, int ny, int nz, int halo_s, int halo_l,
+                              int theta_to_t0, const sbd_params* prm, uint8_t* flags)
+{
+  if (nx < 1 || ny < 1 || nz < 1) return fail(SBD_EDIMS, "rows, row_length, levels must be >= 1");   // U:198-201: error = 1
+  if (!pp || !u || !v || !theta || !z || !sigma || !mask || !windspeed || !winddir || !thc || !sb_con)
+    return fail(SBD_EINVAL, "NULL argument");
+  if (halo_s < 1 || halo_l < 1) return fail(SBD_EINVAL, "halo widths must be >= 1");
+  int rc = ensure_device();
+  if (rc) return rc;
+  sbd_params q;
+  if (prm) q = *prm;
+  else { sbd_default_params(&q, SBD_VARIANT_GENERIC); q.level_scan = 1; }     // U:265-274: early-exit level search
+  const int h = std::min(halo_s, halo_l);     // the window search may reach as far as BOTH kinds of plane have data
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  sbd_plan* p = cache_find_or_create(SBD_VARIANT_GENERIC, nx, ny, nz, h, q, &rc);
+  if (!p) return rc;
+  Tmp t;
+  t.st = p->stream;
+  const size_t ns = (size_t)(nx + 2 * halo_s) * (ny + 2 * halo_s), nl = (size_t)(nx + 2 * halo_l) * (ny + 2 * halo_l);
+  const size_t nh = (size_t)(nx + 2 * h) * (ny + 2 * h);
+  const float *d_z, *d_sigma, *d_mask;
+  void* d_theta;
+  if ((rc = t.out(theta, ns * 4, true, &d_theta))) return rc;
+  if (!theta_to_t0 && !is_device_ptr(theta)) t.pend.pop_back();   // theta is not modified: nothing to copy back
+  if ((rc = t.in(z, ns, &d_z))) return rc;
+  if ((rc = t.in(sigma, ns, &d_sigma))) return rc;
+  if ((rc = t.in(mask, nl, &d_mask))) return rc;
+  const float *c_theta = (const float*)d_theta, *c_z = d_z, *c_sigma = d_sigma, *c_mask = d_mask;
+  dim3 g(cdiv(nx + 2 * h, 128), ny + 2 * h);
+  if (halo_s != h) {
+    void *a, *b, *c;
+    if ((rc = t.scratch(nh * 4, &a)) || (rc = t.scratch(nh * 4, &b)) || (rc = t.scratch(nh * 4, &c))) return rc;
+    k_crop_halo<<<g, 128, 0, t.st>>>((float*)a, (const float*)d_theta, nx, ny, h, halo_s, halo_s); LAUNCHED();
+    k_crop_halo<<<g, 128, 0, t.st>>>((float*)b, d_z, nx, ny, h, halo_s, halo_s); LAUNCHED();
+    k_crop_halo<<<g, 128, 0, t.st>>>((float*)c, d_sigma, nx, ny, h, halo_s, halo_s); LAUNCHED();
+    c_theta = (const float*)a; c_z = (const float*)b; c_sigma = (const float*)c;
+  }
+  if (halo_l != h) {
+    void* a;
+    if ((rc = t.scratch(nh * 4, &a))) return rc;
+    k_crop_halo<<<g, 128, 0, t.st>>>((float*)a, d_mask, nx, ny, h, halo_l, halo_l); LAUNCHED();
+    c_mask = (const float*)a;
+  }
+  CK(cudaGetLastError());
+  if ((rc = set_static_cached(p, c_mask, c_z, c_sigma))) return rc;
+  if ((rc = sbd_plan_step(p, timestep, timestep_number, pp, u, v, c_theta, windspeed, winddir, thc, sb_con, flags))) return rc;
+  if (theta_to_t0) {
+    // U:210-211: theta = theta - gmma * z * smod_sigma over the whole small-halo array (statistics: interior)
+    k_um_t0_inplace<<<(unsigned)((ns + 255) / 256), 256, 0, t.st>>>((float*)d_theta, d_z, d_sigma, (long long)ns, p->d_stats,
+                                                                   p->prm.gmma); LAUNCHED();
+    CK(cudaGetLastError());
+  }
   return t.finish();
 }
 

@@ -93,6 +93,19 @@ contains
     integer(c_int) :: nx, ny, nz, h
     nx = size(p, 1); ny = size(p, 2); nz = size(p, 3)
     h = (size(mask, 1) - nx) / 2          ! halo'd neighbour fields (UM tdims_s / tdims_l)
+    ! The C side reads (nx + 2h) x (ny + 2h) elements of every neighbour-read field: refuse anything else.  NOTE
+    ! that generic/get_all_fields_mod.f90:17-19 declares mask, theta as (nx+halo, ny+halo) and z, sigma as (nx, ny):
+    ! those arrays are NOT conformable with this interface (nor with G:167 itself, SURVEY.md A.6) -- allocate all
+    ! four with 2*halo_size extra points in both directions, as the UM does (U:78-117).
+    if (h < 1 .or. size(mask, 1) /= nx + 2 * h .or. size(mask, 2) /= ny + 2 * h) &
+      error stop 'sea_breeze_diag_mod: mask must be (nx + 2*halo, ny + 2*halo), halo >= 1'
+    if (any(shape(theta) /= shape(mask)) .or. any(shape(z) /= shape(mask)) .or. any(shape(sigma) /= shape(mask))) &
+      error stop 'sea_breeze_diag_mod: theta, z, sigma and mask must share the shape (nx + 2*halo, ny + 2*halo)'
+    if (any(shape(u) /= shape(p)) .or. any(shape(v) /= shape(p))) &
+      error stop 'sea_breeze_diag_mod: p, u, v must share one shape'
+    if (any(shape(windspeed) /= (/nx, ny/)) .or. any(shape(winddir) /= (/nx, ny/)) .or. &
+        any(shape(thc) /= (/nx, ny/)) .or. any(shape(sb_con) /= (/nx, ny/))) &
+      error stop 'sea_breeze_diag_mod: windspeed, winddir, thc, sb_con must be (nx, ny)'
     call check(sbd_seabreeze_diag_f32(timestep, timestep_number, p, u, v, theta, mask, z, sigma, &
                windspeed, winddir, thc, sb_con, nx, ny, nz, h, c_null_ptr, c_null_ptr), 'seabreeze_diag')
   end subroutine seabreeze_diag
@@ -102,6 +115,10 @@ contains
     real, intent(inout), contiguous :: mask(:, :)
     real, intent(in), contiguous :: icefrac(:, :), landfrac(:, :)
     integer, intent(in) :: halo_size
+    if (halo_size < 1 .or. size(mask, 1) /= size(landfrac, 1) + 2 * halo_size .or. &
+        size(mask, 2) /= size(landfrac, 2) + 2 * halo_size) &
+      error stop 'sea_breeze_diag_mod: get_edges needs mask(nx + 2*halo_size, ny + 2*halo_size)'
+    if (any(shape(icefrac) /= shape(landfrac))) error stop 'sea_breeze_diag_mod: icefrac and landfrac differ in shape'
     call check(sbd_get_edges_f32(mask, icefrac, landfrac, size(landfrac, 1), size(landfrac, 2), &
                halo_size, 1_c_int, c_null_ptr), 'get_edges')
   end subroutine get_edges
@@ -112,6 +129,11 @@ contains
     real, intent(in) :: maxdist
     real, intent(out), contiguous :: cdist(:, :)
     integer, intent(in) :: halo_size
+    if (size(coast, 1) /= size(lon, 1) + 2 * halo_size .or. size(coast, 2) /= size(lat, 1) + 2 * halo_size) &
+      error stop 'sea_breeze_diag_mod: get_dist needs coast(nx + 2*halo_size, ny + 2*halo_size) (output of get_edges)'
+    if (size(landfrac, 1) /= size(lon, 1) .or. size(landfrac, 2) /= size(lat, 1) .or. &
+        any(shape(cdist) /= shape(landfrac))) &
+      error stop 'sea_breeze_diag_mod: get_dist needs landfrac(nx, ny) and cdist(nx, ny)'
     call check(sbd_get_dist_f32(coast, landfrac, lon, lat, maxdist, cdist, size(lon, 1), size(lat, 1), &
                halo_size), 'get_dist')
   end subroutine get_dist

@@ -128,14 +128,16 @@ int sbd_swap_bounds_f32(float* field, int nx, int ny, int h);
 /* ---- 64-bit REAL twins ------------------------------------------
  * For hosts compiled with promoted reals (the UM's usual -r8 build: real(kind=jprb) at
  * UM/vn10.7/sea_breeze_diag.F90:64).  Same arguments as the _f32 routines with double arrays and
- * scalars (host or device pointers).  The arrays are narrowed to fp32 on the device (round to
- * nearest), the fp32 kernels run unchanged, and the results are widened exactly, so
- *   twin(x) == widen(f32 routine(narrow(x)))  bit for bit,
- * and for inputs that are exactly representable in fp32 the twin reproduces the fp32 results.
- * Against an evaluation that keeps 64 bits throughout, the floating-point diagnostics agree to
- * fp32 accuracy (tests/test_gpu_f64.py: relative 2e-4 on sb_con, thc, windspeed; 2e-3 degrees on
- * winddir) and the trigger flag can differ only where a quantity sits within fp32 rounding of its
- * threshold.  No 64-bit arithmetic kernels exist in this round. */
+ * scalars (host or device pointers).
+ *   sbd_seabreeze_diag_f64, sbd_sigmoid_f64 (and sbd_um_seabreeze_diag_f64): evaluated in BINARY64 THROUGHOUT --
+ *     sequential statistics, t0, window sums in the reference's raster order, level search, wind, thresholds,
+ *     scaling, state (csrc/sbd_f64.cuh; U:144-150 accumulate in jprb).  Plain one-thread-per-cell kernels: this is
+ *     the correctness path for -r8 hosts, not the tuned fp32 path.  Against a float64 evaluation the results agree
+ *     to ~1e-12 relative (CUDA's binary64 exp / atan2 vs glibc's); tests/test_gpu_f64.py states the tolerances.
+ *   sbd_get_edges_f64, sbd_get_dist_f64, sbd_swap_bounds_f64 (static, one-off work): the arrays are narrowed to
+ *     fp32 on the device, the fp32 kernels run, the results are widened exactly:
+ *     twin(x) == widen(f32 routine(narrow(x))) bit for bit; coast distances agree with a 64-bit evaluation to
+ *     fp32 accuracy. */
 int sbd_get_edges_f64(double* mask, const double* icefrac, const double* landfrac, int nx, int ny, int h,
                       int swap);
 int sbd_get_dist_f64(const double* coast, const double* landfrac, const double* lon, const double* lat,
@@ -181,6 +183,18 @@ int sbd_um_get_dist_f32(const float* landfrac, float* coast, const float* true_l
  * the UM), single domain: east-west periodic, north-south edge rows.  fld_type / l_vector do not matter for scalars
  * on one domain; between GPUs see seabreeze_param_b200/halo.py. */
 int sbd_um_swap_bounds_f32(float* field, int row_len, int rows, int levels, int halo_i, int halo_j);
+
+/* 64-bit REAL twins of the four UM entry points (fortran/sea_breeze_diag_um.F90 compiled with -DSBD_R8):
+ * seabreeze_diag in binary64 throughout, the other three as described for the _f64 twins above. */
+int sbd_um_seabreeze_diag_f64(double timestep, int timestep_number, const double* p, const double* u, const double* v,
+                              double* theta, const double* z, const double* sigma, const double* mask, double* windspeed,
+                              double* winddir, double* thc, double* sb_con, int row_length, int rows, int levels,
+                              int halo_s, int halo_l, int theta_to_t0, const sbd_params* prm, uint8_t* flags);
+int sbd_um_get_edges_f64(double* mask, const double* icefrac, const double* landfrac, int row_length, int rows,
+                         int halo_i, int halo_j);
+int sbd_um_get_dist_f64(const double* landfrac, double* coast, const double* true_latitude, const double* true_longitude,
+                        int row_length, int rows, int halo_i, int halo_j, double maxdist);
+int sbd_um_swap_bounds_f64(double* field, int row_len, int rows, int levels, int halo_i, int halo_j);
 
 /* ---------------------------------------------------------------------------------------------
  * Python (f2py module `seabreeze`) entry points: same positional meaning as the f2py signatures.

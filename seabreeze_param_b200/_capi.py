@@ -26,6 +26,7 @@ SYMBOLS = [
     "sbd_get_edges_f64", "sbd_get_dist_f64", "sbd_sigmoid_f64", "sbd_seabreeze_diag_f64", "sbd_swap_bounds_f64",
     "sbd_plan_cache_clear", "sbd_plan_cache_stats", "sbd_host_register", "sbd_host_unregister",
     "sbd_um_seabreeze_diag_f32", "sbd_um_get_edges_f32", "sbd_um_get_dist_f32", "sbd_um_swap_bounds_f32",
+    "sbd_um_seabreeze_diag_f64", "sbd_um_get_edges_f64", "sbd_um_get_dist_f64", "sbd_um_swap_bounds_f64",
 ]
 
 
@@ -124,6 +125,10 @@ def load():
     lib.sbd_um_get_edges_f32.argtypes = [fp, fp, fp, i, i, i, i]
     lib.sbd_um_get_dist_f32.argtypes = [fp, fp, fp, fp, i, i, i, i, f]
     lib.sbd_um_swap_bounds_f32.argtypes = [fp, i, i, i, i, i]
+    lib.sbd_um_seabreeze_diag_f64.argtypes = [C.c_double, i] + [vp] * 11 + [i, i, i, i, i, i, C.POINTER(SbdParams), vp]
+    lib.sbd_um_get_edges_f64.argtypes = [vp, vp, vp, i, i, i, i]
+    lib.sbd_um_get_dist_f64.argtypes = [vp, vp, vp, vp, i, i, i, i, C.c_double]
+    lib.sbd_um_swap_bounds_f64.argtypes = [vp, i, i, i, i, i]
     _LIB = lib
     return lib
 

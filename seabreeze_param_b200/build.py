@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "sbd_cuda.cu")
 OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libsbd_b200.so")
-DEPS = [SRC, os.path.join(HERE, "csrc", "sbd_win8.cuh"), os.path.join(HERE, "csrc", "sbd_um.cuh"), os.path.join(ROOT, "include", "sbd.h"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "sbd_win8.cuh"), os.path.join(HERE, "csrc", "sbd_um.cuh"), os.path.join(HERE, "csrc", "sbd_f64.cuh"), os.path.join(ROOT, "include", "sbd.h"),
         os.path.join(ROOT, "include", "sbd_math.h")]
 
 NVCC_FLAGS = [

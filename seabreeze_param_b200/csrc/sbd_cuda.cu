@@ -2065,6 +2065,7 @@ __global__ void k_widen(const float* __restrict__ src, double* __restrict__ dst,
 }
 
 #include "sbd_um.cuh"
+#include "sbd_f64.cuh"
 
 }  // namespace sbdk
 using namespace sbdk;
@@ -3601,18 +3602,105 @@ int sbd_get_dist_f64(const double* coast, const double* land, const double* lon,
   return t.finish();
 }
 
+// device view of a 64-bit input / inout array (host arrays are staged)
+namespace {
+struct Tmp64d {
+  cudaStream_t st = nullptr;
+  std::vector<void*> bufs;
+  struct Out { void* user; void* dev; size_t bytes; };
+  std::vector<Out> outs;
+  ~Tmp64d() { for (void* b : bufs) cudaFree(b); }
+  int alloc(size_t bytes, void** d) { CK(cudaMalloc(d, bytes)); bufs.push_back(*d); return SBD_OK; }
+  int in(const double* src, size_t n, const double** out)
+  {
+    if (is_device_ptr(src)) { *out = src; return SBD_OK; }
+    void* d; int rc = alloc(n * 8, &d); if (rc) return rc;
+    CK(cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, st));
+    *out = (const double*)d; return SBD_OK;
+  }
+  int out(double* dst, size_t n, bool copy_in, double** o)
+  {
+    if (is_device_ptr(dst)) { *o = dst; return SBD_OK; }
+    void* d; int rc = alloc(n * 8, &d); if (rc) return rc;
+    if (copy_in) CK(cudaMemcpyAsync(d, dst, n * 8, cudaMemcpyHostToDevice, st));
+    outs.push_back({dst, d, n * 8}); *o = (double*)d; return SBD_OK;
+  }
+  int finish()
+  {
+    for (auto& o : outs) CK(cudaMemcpyAsync(o.user, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return SBD_OK;
+  }
+};
+
+// seabreeze_diag in binary64 on device planes: theta, z, sigma with halo hs, mask with halo hl (UM: tdims_s / tdims_l;
+// generic: hs == hl).  theta_out != nullptr: t0 is also written there over the whole halo-hs plane (U:210-211).
+int diag64_device(Tmp64d& t, double timestep, int step, const double* d_p, const double* d_u, const double* d_v,
+                  const double* d_theta, double* d_theta_out, const double* d_z, const double* d_sigma, const double* d_mask,
+                  double* d_ws, double* d_wd, double* d_thc, double* d_sb, int nx, int ny, int nz, int hs, int hl,
+                  const sbd_params& q, uint8_t* flags)
+{
+  int rc;
+  const int h = std::min(hs, hl);
+  const size_t ns = (size_t)(nx + 2 * hs) * (ny + 2 * hs), nh = (size_t)(nx + 2 * h) * (ny + 2 * h);
+  void *d_st, *d_t0s;
+  if ((rc = t.alloc(4 * sizeof(double), &d_st)) || (rc = t.alloc(ns * 8, &d_t0s))) return rc;
+  // statistics over the interior, sequential order, binary64
+  k64_stats_seq<<<1, 32, 0, t.st>>>(d_sigma + (size_t)hs * (nx + 2 * hs) + hs, nx, ny, nx + 2 * hs, (double*)d_st); LAUNCHED();
+  k64_t0<<<(unsigned)((ns + 255) / 256), 256, 0, t.st>>>(d_theta, d_z, d_sigma, (double*)d_t0s, (long long)ns, (const double*)d_st,
+                                                        (double)q.gmma); LAUNCHED();
+  const double* c_t0 = (const double*)d_t0s;
+  const double* c_mask = d_mask;
+  dim3 gc(cdiv(nx + 2 * h, 128), ny + 2 * h);
+  if (hs != h) {
+    void* a; if ((rc = t.alloc(nh * 8, &a))) return rc;
+    k64_crop_halo<<<gc, 128, 0, t.st>>>((double*)a, (const double*)d_t0s, nx, ny, h, hs); LAUNCHED();
+    c_t0 = (const double*)a;
+  }
+  if (hl != h) {
+    void* a; if ((rc = t.alloc(nh * 8, &a))) return rc;
+    k64_crop_halo<<<gc, 128, 0, t.st>>>((double*)a, d_mask, nx, ny, h, hl); LAUNCHED();
+    c_mask = (const double*)a;
+  }
+  uint8_t* d_flags = flags;
+  void* d_fl_stage = nullptr;
+  if (flags && !is_device_ptr(flags)) { if ((rc = t.alloc((size_t)nx * ny, &d_fl_stage))) return rc; d_flags = (uint8_t*)d_fl_stage; }
+  Diag64Args a{};
+  a.nx = nx; a.ny = ny; a.nz = nz; a.h = h; a.ldx = nx + 2 * h;
+  a.first_step = step < 2 ? 1 : 0;
+  {
+    double r = fmod((double)step * timestep, (double)q.target_time);
+    if (r != 0.0 && ((r < 0.0) != ((double)q.target_time < 0.0))) r += (double)q.target_time;
+    a.six_hourly = r < 0.0001 ? 1 : 0;                          // G:264
+  }
+  a.level_scan = q.level_scan;
+  a.target_plev = q.target_plev; a.thresh_wind = q.thresh_wind; a.thresh_winddir = q.thresh_winddir;
+  a.thresh_windch = q.thresh_windch; a.thresh_thc = q.thresh_thc; a.maxdist = q.maxdist;
+  a.rad2deg = 57.2957; a.missing = q.missing;                    // the source's literal constants (G:128-138)
+  a.p = d_p; a.u = d_u; a.v = d_v; a.t0 = c_t0; a.mask = c_mask;
+  a.ws = d_ws; a.wd = d_wd; a.thc = d_thc; a.sb = d_sb; a.flags = d_flags;
+  dim3 g(cdiv(nx, 128), ny);
+  k64_diag<<<g, 128, 0, t.st>>>(a); LAUNCHED();
+  if (d_theta_out) CK(cudaMemcpyAsync(d_theta_out, d_t0s, ns * 8, cudaMemcpyDeviceToDevice, t.st));
+  if (d_fl_stage) CK(cudaMemcpyAsync(flags, d_fl_stage, (size_t)nx * ny, cudaMemcpyDeviceToHost, t.st));
+  CK(cudaGetLastError());
+  return SBD_OK;
+}
+}  // namespace
+
 int sbd_sigmoid_f64(const double* ary, double* sm, int nx, int ny)
 {
   if (!ary || !sm) return fail(SBD_EINVAL, "NULL argument");
   if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
   int rc = ensure_device();
   if (rc) return rc;
-  Tmp64 t;
-  const size_t n2 = (size_t)nx * ny;
-  float *d_ary, *d_sm;
-  if ((rc = t.in(ary, n2, &d_ary)) || (rc = t.out(sm, n2, false, &d_sm))) return rc;
-  CK(cudaStreamSynchronize(t.st));
-  if ((rc = sbd_sigmoid_f32(d_ary, d_sm, nx, ny, nullptr))) return rc;
+  Tmp64d t;
+  const size_t n = (size_t)nx * ny;
+  const double* d_a; double* d_sm; void* d_st;
+  if ((rc = t.in(ary, n, &d_a)) || (rc = t.out(sm, n, false, &d_sm)) || (rc = t.alloc(4 * sizeof(double), &d_st))) return rc;
+  k64_stats_seq<<<1, 32, 0, t.st>>>(d_a, nx, ny, nx, (double*)d_st); LAUNCHED();
+  k64_sigmoid_apply<<<(unsigned)((n + 255) / 256), 256, 0, t.st>>>(d_a, d_sm, (long long)n, (const double*)d_st); LAUNCHED();
   return t.finish();
 }
 
@@ -3637,19 +3725,21 @@ int sbd_seabreeze_diag_f64(double timestep, int step, const double* pp, const do
   if (!pp || !u || !v || !theta || !mask || !z || !sigma || !ws || !wd || !thc || !sb)
     return fail(SBD_EINVAL, "NULL argument");
   if (nx < 1 || ny < 1 || nz < 1) return fail(SBD_EDIMS, "bad dims");   // U:198-201 -> error = 1
-  if (h < 0) return fail(SBD_EINVAL, "bad halo");
+  if (h < 1) return fail(SBD_EINVAL, "bad halo");
   int rc = ensure_device();
   if (rc) return rc;
-  Tmp64 t;
+  sbd_params q;
+  if (prm) q = *prm; else sbd_default_params(&q, SBD_VARIANT_GENERIC);
+  Tmp64d t;
   const size_t n2 = (size_t)nx * ny, n3 = n2 * nz, nh = (size_t)(nx + 2 * h) * (ny + 2 * h);
-  float *d_p, *d_u, *d_v, *d_th, *d_mk, *d_z, *d_sg, *d_ws, *d_wd, *d_thc, *d_sb;
+  const double *d_p, *d_u, *d_v, *d_th, *d_mk, *d_z, *d_sg;
+  double *d_ws, *d_wd, *d_thc, *d_sb;
   if ((rc = t.in(pp, n3, &d_p)) || (rc = t.in(u, n3, &d_u)) || (rc = t.in(v, n3, &d_v)) ||
       (rc = t.in(theta, nh, &d_th)) || (rc = t.in(mask, nh, &d_mk)) || (rc = t.in(z, nh, &d_z)) ||
       (rc = t.in(sigma, nh, &d_sg)) || (rc = t.out(ws, n2, true, &d_ws)) || (rc = t.out(wd, n2, true, &d_wd)) ||
       (rc = t.out(thc, n2, true, &d_thc)) || (rc = t.out(sb, n2, true, &d_sb))) return rc;
-  CK(cudaStreamSynchronize(t.st));
-  if ((rc = sbd_seabreeze_diag_f32((float)timestep, step, d_p, d_u, d_v, d_th, d_mk, d_z, d_sg, d_ws, d_wd, d_thc,
-                                   d_sb, nx, ny, nz, h, prm, flags))) return rc;
+  if ((rc = diag64_device(t, timestep, step, d_p, d_u, d_v, d_th, nullptr, d_z, d_sg, d_mk, d_ws, d_wd, d_thc, d_sb,
+                          nx, ny, nz, h, h, q, flags))) return rc;
   return t.finish();
 }
 
@@ -3791,6 +3881,86 @@ int sbd_um_seabreeze_diag_f32(float timestep, int timestep_number, const float* 
                                                                    p->prm.gmma); LAUNCHED();
     CK(cudaGetLastError());
   }
+  return t.finish();
+}
+
+// 64-bit REAL twins of the UM entry points (fortran/sea_breeze_diag_um.F90 with -DSBD_R8).  seabreeze_diag runs in
+// binary64 throughout (sbd_f64.cuh); get_edges / get_dist / swap_bounds -- small-integer and one-off work -- narrow to
+// fp32 on the device, run the fp32 kernels and widen exactly (the comparison thresholds 0.2 / 0.5 of get_edges are
+// applied to the narrowed values: a fraction within 1e-8 of a threshold can binarise differently).
+int sbd_um_seabreeze_diag_f64(double timestep, int timestep_number, const double* pp, const double* u, const double* v,
+                              double* theta, const double* z, const double* sigma, const double* mask, double* windspeed,
+                              double* winddir, double* thc, double* sb_con, int nx, int ny, int nz, int halo_s, int halo_l,
+                              int theta_to_t0, const sbd_params* prm, uint8_t* flags)
+{
+  if (nx < 1 || ny < 1 || nz < 1) return fail(SBD_EDIMS, "rows, row_length, levels must be >= 1");   // U:198-201
+  if (!pp || !u || !v || !theta || !z || !sigma || !mask || !windspeed || !winddir || !thc || !sb_con)
+    return fail(SBD_EINVAL, "NULL argument");
+  if (halo_s < 1 || halo_l < 1) return fail(SBD_EINVAL, "halo widths must be >= 1");
+  int rc = ensure_device();
+  if (rc) return rc;
+  sbd_params q;
+  if (prm) q = *prm;
+  else { sbd_default_params(&q, SBD_VARIANT_GENERIC); q.level_scan = 1; }
+  Tmp64d t;
+  const size_t n2 = (size_t)nx * ny, n3 = n2 * nz;
+  const size_t ns = (size_t)(nx + 2 * halo_s) * (ny + 2 * halo_s), nl = (size_t)(nx + 2 * halo_l) * (ny + 2 * halo_l);
+  const double *d_p, *d_u, *d_v, *d_z, *d_sg, *d_mk;
+  double *d_th, *d_ws, *d_wd, *d_thc, *d_sb;
+  if ((rc = t.in(pp, n3, &d_p)) || (rc = t.in(u, n3, &d_u)) || (rc = t.in(v, n3, &d_v)) ||
+      (rc = t.out(theta, ns, true, &d_th)) || (rc = t.in(z, ns, &d_z)) || (rc = t.in(sigma, ns, &d_sg)) ||
+      (rc = t.in(mask, nl, &d_mk)) || (rc = t.out(windspeed, n2, true, &d_ws)) || (rc = t.out(winddir, n2, true, &d_wd)) ||
+      (rc = t.out(thc, n2, true, &d_thc)) || (rc = t.out(sb_con, n2, true, &d_sb))) return rc;
+  if ((rc = diag64_device(t, timestep, timestep_number, d_p, d_u, d_v, d_th, theta_to_t0 ? d_th : nullptr, d_z, d_sg, d_mk,
+                          d_ws, d_wd, d_thc, d_sb, nx, ny, nz, halo_s, halo_l, q, flags))) return rc;
+  return t.finish();
+}
+
+int sbd_um_get_edges_f64(double* mask, const double* icefrac, const double* landfrac, int nx, int ny, int halo_i, int halo_j)
+{
+  if (!mask || !icefrac || !landfrac) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp64 t;
+  const size_t n2 = (size_t)nx * ny, nl = (size_t)(nx + 2 * halo_i) * (ny + 2 * halo_j);
+  float *d_ice, *d_land, *d_mask;
+  if ((rc = t.in(icefrac, n2, &d_ice)) || (rc = t.in(landfrac, n2, &d_land)) || (rc = t.out(mask, nl, true, &d_mask))) return rc;
+  CK(cudaStreamSynchronize(t.st));
+  if ((rc = sbd_um_get_edges_f32(d_mask, d_ice, d_land, nx, ny, halo_i, halo_j))) return rc;
+  return t.finish();
+}
+
+int sbd_um_get_dist_f64(const double* landfrac_l, double* coast_l, const double* true_latitude, const double* true_longitude,
+                        int nx, int ny, int halo_i, int halo_j, double maxdist)
+{
+  if (!landfrac_l || !coast_l || !true_latitude || !true_longitude) return fail(SBD_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1) return fail(SBD_EDIMS, "bad dims");
+  int rc = ensure_device();
+  if (rc) return rc;
+  Tmp64 t;
+  const size_t n2 = (size_t)nx * ny, nl = (size_t)(nx + 2 * halo_i) * (ny + 2 * halo_j);
+  float *d_land, *d_coast, *d_lat, *d_lon;
+  if ((rc = t.in(landfrac_l, nl, &d_land)) || (rc = t.out(coast_l, nl, true, &d_coast)) ||
+      (rc = t.in(true_latitude, n2, &d_lat)) || (rc = t.in(true_longitude, n2, &d_lon))) return rc;
+  CK(cudaStreamSynchronize(t.st));
+  if ((rc = sbd_um_get_dist_f32(d_land, d_coast, d_lat, d_lon, nx, ny, halo_i, halo_j, (float)maxdist))) return rc;
+  return t.finish();
+}
+
+int sbd_um_swap_bounds_f64(double* field, int row_len, int rows, int levels, int halo_i, int halo_j)
+{
+  if (!field) return fail(SBD_EINVAL, "NULL argument");
+  if (row_len < 1 || rows < 1 || levels < 1) return fail(SBD_EDIMS, "bad dims");
+  int rc = ensure_device();
+  if (rc) return rc;
+  // pure data movement: done on the 64-bit values themselves (two 32-bit halves move together)
+  Tmp64d t;
+  const size_t n = (size_t)(row_len + 2 * halo_i) * (rows + 2 * halo_j) * levels;
+  double* d;
+  if ((rc = t.out(field, n, true, &d))) return rc;
+  // view every double as two floats: a plane of 2 (row_len + 2 halo_i) floats per row with halo 2 halo_i
+  if ((rc = um_halo_fill(t.st, (float*)d, 2 * row_len, rows, 2 * halo_i, halo_j, levels))) return rc;
   return t.finish();
 }
 

@@ -1,7 +1,8 @@
 """64-bit REAL mirrors of sea_breeze_diag_mod for hosts built with promoted reals (UM -r8;
 UM/vn10.7/sea_breeze_diag.F90:64 real(kind=jprb)).  Same routines and argument order as
-seabreeze_param_b200.generic, float64 numpy arrays; everything runs through the _f64 twins of the
-C-ABI (include/sbd.h): narrowed to fp32 on the device, fp32 kernels, exact widening."""
+seabreeze_param_b200.generic, float64 numpy arrays, through the _f64 entry points of the C-ABI (include/sbd.h):
+sigmoid and seabreeze_diag run in binary64 throughout (csrc/sbd_f64.cuh); get_edges, get_dist and swap_bounds --
+static, one-off work on small integers / coast distances -- are narrowed to fp32 on the device and widened exactly."""
 import ctypes as C
 
 import numpy as np

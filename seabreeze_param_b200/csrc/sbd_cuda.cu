@@ -3648,8 +3648,11 @@ int diag64_device(Tmp64d& t, double timestep, int step, const double* d_p, const
   if ((rc = t.alloc(4 * sizeof(double), &d_st)) || (rc = t.alloc(ns * 8, &d_t0s))) return rc;
   // statistics over the interior, sequential order, binary64
   k64_stats_seq<<<1, 32, 0, t.st>>>(d_sigma + (size_t)hs * (nx + 2 * hs) + hs, nx, ny, nx + 2 * hs, (double*)d_st); LAUNCHED();
+  // sbd_params carries binary32 tunables; the source's literal -0.0060956 (G:138) is taken at binary64 precision
+  // when the parameter still is the default
+  const double gmma64 = (q.gmma == -0.0060956f) ? -0.0060956 : (double)q.gmma;
   k64_t0<<<(unsigned)((ns + 255) / 256), 256, 0, t.st>>>(d_theta, d_z, d_sigma, (double*)d_t0s, (long long)ns, (const double*)d_st,
-                                                        (double)q.gmma); LAUNCHED();
+                                                        gmma64); LAUNCHED();
   const double* c_t0 = (const double*)d_t0s;
   const double* c_mask = d_mask;
   dim3 gc(cdiv(nx + 2 * h, 128), ny + 2 * h);

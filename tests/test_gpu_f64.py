@@ -147,8 +147,9 @@ def test_um_f64_entry_point_two_halo_widths(oracle):
                       *st_r, hs)
         th = d(theta_h)
         fg = np.zeros((ny, nx), np.uint8)
-        rc = lib.sbd_um_seabreeze_diag_f64(C.c_double(cfg.timestep), step, q(d(p)), q(d(u)), q(d(v)), q(th), q(d(case["z_h"])),
-                                           q(d(case["sigma_h"])), q(mask_l), *[q(a) for a in st_g], nx, ny, cfg.nz, hs, hl, 1,
+        p64, u64, v64, z64, sg64 = d(p), d(u), d(v), d(case["z_h"]), d(case["sigma_h"])   # keep the arrays alive
+        rc = lib.sbd_um_seabreeze_diag_f64(C.c_double(cfg.timestep), step, q(p64), q(u64), q(v64), q(th), q(z64),
+                                           q(sg64), q(mask_l), *[q(a) for a in st_g], nx, ny, cfg.nz, hs, hl, 1,
                                            None, q(fg))
         assert rc == 0
         assert int((fr != fg).sum()) <= 1

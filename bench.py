@@ -196,6 +196,28 @@ def timed_steps(ctx, one_step, k0, warmup, steps, sample_clocks=True):
     return total_ms, k, clocks
 
 
+def balanced_rows(cost_per_row, world, align=32, min_rows=1):
+    """Row-block boundaries [r_0 = 0, r_1, ..., r_world = ny] that equalise the summed cost per block; interior
+    boundaries sit on multiples of `align` (the window kernels' tile height: no partial tiles at block edges)."""
+    ny = len(cost_per_row)
+    pre = np.concatenate([[0.0], np.cumsum(np.asarray(cost_per_row, np.float64))])
+    bounds = [0]
+    for k in range(1, world):
+        r = int(np.searchsorted(pre, pre[-1] * k / world))
+        r = int(round(r / align)) * align
+        r = max(r, bounds[-1] + max(min_rows, align))
+        r = min(r, ny - (world - k) * max(min_rows, align))
+        bounds.append(r)
+    bounds.append(ny)
+    return bounds
+
+
+def window_cost_rows(nn, per_cell):
+    """static cost model of a latitude row: window elements of its coastal-zone cells + a per-cell constant"""
+    nn = nn.astype(np.float64)
+    return ((2.0 * nn + 1.0) ** 2 * (nn > 0)).sum(axis=1) + per_cell * nn.shape[1]
+
+
 # ======================================================================================================
 # deterministic device-side generators (a function of GLOBAL position only: every decomposition sees the same grid)
 # ======================================================================================================
@@ -525,13 +547,27 @@ def bench_c3(ctx, args, steps, warmup, short=False):
     cfg = synth.CONFIGS["c3"]
     world, rank, dev, dist = ctx.world, ctx.rank, ctx.dev, ctx.dist
     h, nx, ny, nz = cfg.h, cfg.nx, cfg.ny, cfg.nz
-    if ny % world:
-        raise SystemExit("c3: %d rows do not split into %d equal blocks" % (ny, world))
-    nyl = ny // world
-    r0, r1 = rank * nyl, (rank + 1) * nyl
     nsets = 1 if world == 1 else 2     # one set of p,u,v is 10 GB / N per rank: far beyond L2 already
     G = C3Grid(ctx, cfg)
     n_cells = nx * ny
+    # Row blocks of EQUAL WORK, not equal height: the search radius -- hence the window sums, (2nn+1)^2 adds per
+    # coastal cell -- varies strongly with latitude band.  The radius plane is static, so every rank evaluates it
+    # once on the whole grid (the static chain runs there anyway) and all ranks derive the same boundaries.
+    # BENCH_C3_SPLIT=equal: blocks of equal height (measured at 8 GPUs: 1.04 ms/step, the slowest rank's window
+    # kernel 0.97 ms against a mean of 0.5 ms).
+    plan_s = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, nz, h)
+    plan_s.set_static(G.mk, G.zh, G.sh)
+    nn_g, _, _ = plan_s.window_info()
+    info_full = plan_s.info()
+    plan_s.close()
+    if os.environ.get("BENCH_C3_SPLIT", "work") == "equal" or world == 1:
+        bounds = [round(ny * k / world) for k in range(world + 1)]
+    else:
+        bounds = balanced_rows(window_cost_rows(nn_g, per_cell=60.0), world, align=32, min_rows=h)
+    rows_all = [bounds[k + 1] - bounds[k] for k in range(world)]
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    nyl = r1 - r0
+    nyl_max = max(rows_all)
 
     # ---- rank 0: the whole grid on one GPU (strong-scaling base + the reference bits of the parity check) ----
     base = None
@@ -546,8 +582,8 @@ def bench_c3(ctx, args, steps, warmup, short=False):
         full_inputs = (th1, p1, u1, v1)
         st1 = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(4)]
         fl1 = torch.zeros((ny, nx), dtype=torch.uint8, device=dev)
-        info1 = plan1.info()
-        if world > 1 or True:
+        info1 = info_full
+        if True:
             for s in range(3):
                 plan1.step(cfg.timestep, s + 2, p1, u1, v1, th1, *st1, flags=fl1)
             torch.cuda.synchronize()
@@ -581,12 +617,17 @@ def bench_c3(ctx, args, steps, warmup, short=False):
     plan.set_halo_mode(mode)
     plan.set_static(mk_b, zh_b, sh_b, stats=G.stats)
     info = plan.info()
-    peer = halo.PeerHalo(nsets, nyl, nx, h, rank, world, dev) if world > 1 else None
+    peer = halo.PeerHalo(nsets, nyl_max, nx, h, rank, world, dev) if world > 1 else None   # symmetric: same shape everywhere
+    ny_up = rows_all[rank - 1] if rank > 0 else 0
+
+    def peers(i):
+        up, _, dn = peer.peers(i)
+        return up, ny_up, dn
     dsteps = []
     for s in range(nsets):
         thg = G.theta_h(ctx, s)
         if peer is not None:
-            th = peer.plane(s)
+            th = peer.plane(s)[:nyl + 2 * h]           # this rank's (nyl + 2h)-row plane inside the symmetric buffer
             th.fill_(7.0e30)                           # halo rows owned by a neighbour hold junk: they must not be read
             th[h:h + nyl, :] = thg[r0 + h:r1 + h, :]
         else:
@@ -603,7 +644,7 @@ def bench_c3(ctx, args, steps, warmup, short=False):
     def one_step(k, st=state, fl=flags, first=2):
         th, p, u, v = dsteps[k % nsets]
         if peer is not None:
-            plan.set_peer_theta(*peer.peers(k % nsets))
+            plan.set_peer_theta(*peers(k % nsets))
         plan.step(cfg.timestep, k + first, p, u, v, th, *st, flags=fl)
 
     l0 = ctx.lib.sbd_launch_count()
@@ -635,7 +676,7 @@ def bench_c3(ctx, args, steps, warmup, short=False):
         th, p, u, v = dsteps[0]
         ctx.barrier()                                   # set 0's theta plane of every rank is in place and unread
         if peer is not None:
-            plan.set_peer_theta(*peer.peers(0))
+            plan.set_peer_theta(*peers(0))
         plan.step(cfg.timestep, s, p, u, v, th, *stp, flags=flp)
         plan.sync()
         if rank == 0:
@@ -644,9 +685,14 @@ def bench_c3(ctx, args, steps, warmup, short=False):
             plan1.sync()
         for j, own in enumerate(stp + [flp]):
             if world > 1:
-                parts = [torch.empty_like(own) for _ in range(world)] if rank == 0 else None
-                dist.gather(own, parts, dst=0)
-                got = torch.cat(parts, 0) if rank == 0 else None
+                if rank == 0:
+                    parts = [own] + [torch.empty((rows_all[r], nx), dtype=own.dtype, device=dev) for r in range(1, world)]
+                    for r in range(1, world):
+                        dist.recv(parts[r], src=r)
+                    got = torch.cat(parts, 0)
+                else:
+                    dist.send(own.contiguous(), dst=0)
+                    got = None
             else:
                 got = own
             if rank == 0:
@@ -696,7 +742,6 @@ def bench_c3(ctx, args, steps, warmup, short=False):
         return None
     peak, peak_src = measured_peak()
     # window kernel: sum over coastal cells of (2nn+1)^2 window elements, each advancing two fp32 running sums
-    nn_g, _, _ = plan1.window_info()
     elem_cells = float(((2.0 * nn_g.astype(np.float64) + 1.0) ** 2 * (nn_g > 0)).sum())
     fp32_peak = 148 * 128 * 1.965e9            # scalar FADD lanes / s (scripts/mb_pipes.cu: 120-123 of 128 per clk per SM)
     adds = 2.0 * elem_cells
@@ -719,7 +764,8 @@ def bench_c3(ctx, args, steps, warmup, short=False):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "c3: " + cfg.descr + ", ONE grid over %d rank(s)" % world,
                    "nx": nx, "ny": ny, "nz": nz, "halo": h, "n_coastal_cells": n_coastal_all, "nn_max": info["nn_max"],
-                   "rows_per_rank": nyl, "trigger_cells_last_parity_step": n_trig,
+                   "rows_per_rank": rows_all, "row_split": "equal work (static radius plane), boundaries on multiples of 32 rows"
+                   if world > 1 else "one block", "trigger_cells_last_parity_step": n_trig,
                    "api": "plan step per rank (static chain once per plan, evaluated on the whole grid by every rank)",
                    "l2": "%d input set(s) of p,u,v per rank, %.2f GB each >> 126 MB L2" % (nsets, 3 * 4 * nyl * nx * nz / 1e9),
                    "parallelism": ("latitude row blocks x%d; theta halo rows (54 per side) read from the neighbours' planes "
@@ -784,8 +830,16 @@ def bench_c4(ctx, args, steps, warmup, short=False):
     generic.sigmoid(ds, stats=st4)                     # global sequential statistics of std (P:291-309)
     stats = st4[:3].copy()
     overlap = 24                                        # >= the largest search radius (checked below)
-    per = (ny + world - 1) // world
-    r0, r1 = min(rank * per, ny), min((rank + 1) * per, ny)
+    # row blocks of equal work (static radius plane + a per-cell constant for the pointwise part), see bench_c3
+    if world > 1 and os.environ.get("BENCH_C4_SPLIT", "work") != "equal":
+        plan_s = generic.Plan(SBD_VARIANT_PYTHON, nx, ny, nps)
+        plan_s.set_static(cdist, dz, ds)
+        nn_g, _, _ = plan_s.window_info()
+        plan_s.close()
+        bounds = balanced_rows(window_cost_rows(nn_g, per_cell=150.0), world, align=32, min_rows=overlap)
+    else:
+        bounds = [round(ny * k / world) for k in range(world + 1)]
+    r0, r1 = bounds[rank], bounds[rank + 1]
     a, b = max(0, r0 - overlap), min(ny, r1 + overlap)
     nb = b - a
     plan = generic.Plan(SBD_VARIANT_PYTHON, nx, nb, nps)
@@ -850,7 +904,7 @@ def bench_c4(ctx, args, steps, warmup, short=False):
             plan1.sync()
             del thf, uf, vf
         if world > 1:
-            parts = [torch.empty(5 * (min((j + 1) * per, ny) - min(j * per, ny)) * nx, dtype=torch.float32, device=dev)
+            parts = [torch.empty(5 * (bounds[j + 1] - bounds[j]) * nx, dtype=torch.float32, device=dev)
                      for j in range(world)] if rank == 0 else None
             if rank == 0:
                 parts[0] = own
@@ -862,7 +916,7 @@ def bench_c4(ctx, args, steps, warmup, short=False):
             parts = [own]
         if rank == 0:
             for j in range(world):
-                j0, j1 = min(j * per, ny), min((j + 1) * per, ny)
+                j0, j1 = bounds[j], bounds[j + 1]
                 n4 = 4 * (j1 - j0) * nx
                 ref = torch.cat([fo[s % 2][:, j0:j1].reshape(-1), ff[j0:j1].reshape(-1).to(torch.float32)])
                 # the python variant never processes the global last row (P:165): both sides write the same there
@@ -908,7 +962,7 @@ def bench_c4(ctx, args, steps, warmup, short=False):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "c4: " + cfg.descr + "; a step is one record, %d records resident and cycled" % nrec,
                    "nx": nx, "ny": ny, "nps": nps, "records": nrec, "get_dist_radius": kk.value, "nn_max": info["nn_max"],
-                   "trigger_cells_last_parity_record": n_trig,
+                   "trigger_cells_last_parity_record": n_trig, "rows_per_rank": [bounds[j + 1] - bounds[j] for j in range(world)],
                    "api": "python-variant plan step per record (coast distance / static planes once: sea ice of the synthetic "
                           "records does not change)",
                    "l2": "u, v of one record: %.2f GB per rank" % (2 * 4 * nb * nx * nps / 1e9),

@@ -803,6 +803,32 @@ __global__ void k_static_code(const float* __restrict__ mask, uint16_t* __restri
   code[s] = (uint16_t)c;
 }
 
+// window work of every 64 x 32 tile of the strip kernels: sum of (2nn+1)^2 over its coastal-zone cells (+ a
+// constant per cell for staging and the pointwise part); one CTA per tile
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_tile_cost(const uint16_t* __restrict__ code, Geo g, int ntx, float* __restrict__ cost)
+{
+  constexpr int TX = 64, TY = 32;
+  const int tile = blockIdx.x, tx = tile % ntx, ty = tile / ntx;
+  float acc = 0.0f;
+  for (int t = threadIdx.x; t < TX * TY; t += blockDim.x) {
+    const int gx = tx * TX + t % TX, gy = ty * TY + t / TX;
+    if (gx < g.nx && gy < g.ny) {
+      const float nn = (float)(code[own_index<VARIANT>(g, gx, gy)] & 0x7fffu);
+      acc += (nn > 0.0f) ? (2.0f * nn + 1.0f) * (2.0f * nn + 1.0f) + 64.0f : 8.0f;
+    }
+  }
+  __shared__ float s[8];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.0f;
+    for (int w = 0; w < 8; ++w) tot += s[w];
+    cost[tile] = tot;
+  }
+}
+
 // Static by-product of the search radius: the number of land cells (mask >= 0, "far" cells included)
 // in every coastal-zone cell's final (2nn+1)^2 window, i.e. the reference's counter n_l after its
 // last pass (G:200-203); n_s = (2nn+1)^2 - n_l.  One thread per interior cell, same index map as the
@@ -861,6 +887,10 @@ struct TrigArgs {
   uint32_t* sync_local; uint32_t* sync_up; uint32_t* sync_dn;
   uint32_t sync_seq;
   int strip_min;  // k_win4: smallest strip radius that is walked as a strip (>= 6); below, one cell per thread
+  // strip kernels (64 x 32 tiles): CTA b works on tile tile_order[b]; the list is static and sorted by the tile's
+  // window work, heaviest first, so the light tiles fill the tail of the launch (CTAs are dispatched in order)
+  const int* tile_order;
+  int ntx;
 };
 
 // ---- peer flags over NVLink (system scope) ----
@@ -1544,14 +1574,15 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
   __shared__ int s_cnt[NB], s_off[NB], s_ccnt[NCB], s_coff[NCB];
   __shared__ int s_lev, s_nstrip, s_ncell;
 
-  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int tile = a.tile_order ? (a.tile_order[blockIdx.x] & 0xfffff) : (int)blockIdx.x;   // heaviest tiles first
+  const int x0 = (tile % a.ntx) * TX, y0 = (tile / a.ntx) * TY;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
   if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
 
   if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {  // multi-GPU post / wait, as in k_trigger
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
       __threadfence_system();
       if (a.sync_up) st_release_sys(a.sync_up + 1, a.sync_seq);
       if (a.sync_dn) st_release_sys(a.sync_dn + 0, a.sync_seq);
@@ -2083,6 +2114,9 @@ struct sbd_plan {
   uint16_t* d_code = nullptr;
   uint32_t* d_cl = nullptr;   // land cells in every coastal-zone cell's final window (k_static_counts)
   int row_lo = 0, row_hi = -1;  // sbd_plan_set_row_window (-1: to the end)
+  int* d_tile_order = nullptr; // 64 x 32 tiles of the strip kernels, heaviest window work first (static)
+  int* d_tile_split = nullptr; // k_win8: the same with heavy tiles given to several CTAs (tile | part << 20 | nparts << 26)
+  int n_tile_split = 0;
   int strip_cells = 4;        // sbd_plan_set_strip_cells: cells per strip of k_win8 (4 or 8)
   int window_kernel = 0;      // sbd_plan_set_window_kernel: 0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4)
   float* d_stats = nullptr;   // 4 floats
@@ -2380,7 +2414,9 @@ int launch_win4(sbd_plan* p, TrigArgs& a)
   a.strip_min = 6;   // swept 6 / 10 / 16 / none in round 1: 6 is best on c3s and c4
   auto kern = k_win4<VARIANT, GEN>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+  a.ntx = cdiv(p->nx, TX);
+  a.tile_order = p->d_tile_order;
+  dim3 grid(a.ntx * cdiv(p->ny, TY));
   a.nws = p->d_nws;
   a.nwd = p->d_nwd;
   cudaLaunchConfig_t cfg = {};
@@ -2418,7 +2454,9 @@ int launch_win8_cfg(sbd_plan* p, TrigArgs& a)
   const size_t smem = (size_t)WPmax * (TY + 2 * R) * 4 + TX * TY + (size_t)(TX * TY / 8 + TX * TY / 4 + TX * TY) * 2;
   auto kern = k_win8<VARIANT, GEN, NT, USE8>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(p->nx, TX), cdiv(p->ny, TY));
+  a.ntx = cdiv(p->nx, TX);
+  a.tile_order = p->d_tile_split;
+  dim3 grid(p->n_tile_split);
   a.nws = p->d_nws;
   a.nwd = p->d_nwd;
   cudaLaunchConfig_t cfg = {};
@@ -2598,7 +2636,7 @@ void sbd_plan_destroy(sbd_plan* p)
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->e_copy) cudaEventDestroy(p->e_copy);
   if (p->e_main) cudaEventDestroy(p->e_main);
-  cudaFree(p->d_pfull);
+  cudaFree(p->d_pfull); cudaFree(p->d_tile_order); cudaFree(p->d_tile_split);
   for (int i = 0; i < 3; ++i) cudaFree(p->d_st_in[i]);
   cudaFree(p->d_sum);
   for (auto& s : p->stage) cudaFree(s.first);
@@ -2769,6 +2807,49 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
     LAUNCHED();
   }
   CK(cudaGetLastError());
+  {
+    // launch order of the strip kernels' tiles: by window work, heaviest first
+    const int ntx = cdiv(p->nx, 64), nty = cdiv(p->ny, 32), nt = ntx * nty;
+    float* d_cost = nullptr;
+    CK(cudaMallocAsync((void**)&d_cost, sizeof(float) * nt, st));
+    if (p->variant == SBD_VARIANT_GENERIC) k_tile_cost<SBD_VARIANT_GENERIC><<<nt, 256, 0, st>>>(p->d_code, p->g, ntx, d_cost);
+    else k_tile_cost<SBD_VARIANT_PYTHON><<<nt, 256, 0, st>>>(p->d_code, p->g, ntx, d_cost);
+    LAUNCHED();
+    std::vector<float> cost(nt);
+    CK(cudaMemcpyAsync(cost.data(), d_cost, sizeof(float) * nt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFreeAsync(d_cost, st));
+    std::vector<int> order(nt);
+    for (int i = 0; i < nt; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    CK(cudaFree(p->d_tile_order));
+    p->d_tile_order = nullptr;
+    CK(cudaMalloc((void**)&p->d_tile_order, sizeof(int) * nt));
+    CK(cudaMemcpyAsync(p->d_tile_order, order.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, st));
+    // k_win8: a tile's CTA lives as long as its window sums take (a 64 x 32 tile of radius 50 is 2e7 window
+    // elements: ~0.7 ms of one SM), which bounds the launch from below however many GPUs share the grid.  Tiles
+    // heavier than a third of a CTA slot's fair share are therefore given to several CTAs (each stages the tile
+    // and takes every nparts-th 8-cell strip); entries sorted by work per CTA, heaviest first.
+    double total = 0.0;
+    for (float c : cost) total += c;
+    int nsm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+    const double share = std::max(total / (2.0 * nsm * 3.0), 2.0e5);
+    std::vector<std::pair<float, int>> ents;
+    for (int i = 0; i < nt; ++i) {
+      int np = (int)std::min(16.0, std::max(1.0, std::ceil(cost[i] / share)));
+      for (int k = 0; k < np; ++k) ents.push_back({cost[i] / np, (int)((uint32_t)i | ((uint32_t)k << 20) | ((uint32_t)np << 26))});
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const std::pair<float, int>& x, const std::pair<float, int>& y) { return x.first > y.first; });
+    std::vector<int> split(ents.size());
+    for (size_t i = 0; i < ents.size(); ++i) split[i] = ents[i].second;
+    CK(cudaFree(p->d_tile_split));
+    p->d_tile_split = nullptr;
+    p->n_tile_split = (int)split.size();
+    CK(cudaMalloc((void**)&p->d_tile_split, sizeof(int) * split.size()));
+    CK(cudaMemcpyAsync(p->d_tile_split, split.data(), sizeof(int) * split.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
   if (p->variant == SBD_VARIANT_GENERIC) {
     // compacted list of coastal-zone cells, raster order (static)
     const int n2 = p->nx * p->ny;

@@ -203,13 +203,17 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
   __shared__ int s_c8[NB], s_c4[NB], s_cc[NB], s_o8[NB], s_o4[NB], s_oc[NB];
   __shared__ int s_lev, s_n8, s_n4, s_nc, s_rt, s_bad, s_next;
 
-  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  // launch entry: tile id | part << 20 | nparts << 26.  Heaviest tiles first; a tile whose window work exceeds a fair
+  // share of an SM's time is given to `nparts` CTAs, each of which stages the tile and takes every nparts-th chunk
+  const uint32_t ent = a.tile_order ? (uint32_t)a.tile_order[blockIdx.x] : ((uint32_t)blockIdx.x | (1u << 26));
+  const int tile = (int)(ent & 0xfffffu), part = (int)((ent >> 20) & 0x3fu), nparts = (int)(ent >> 26);
+  const int x0 = (tile % a.ntx) * TX, y0 = (tile / a.ntx) * TY;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
 
   if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {  // multi-GPU post / wait, as in k_trigger
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
       __threadfence_system();
       if (a.sync_up) st_release_sys(a.sync_up + 1, a.sync_seq);
       if (a.sync_dn) st_release_sys(a.sync_dn + 0, a.sync_seq);
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
       const uint32_t cd = a.code[so];
       const int nn = (int)(cd & 0x7fffu);
       const size_t c = (size_t)gy * a.g.nx + gx;
-      if (nn == 0) {  // outside the coastal zone (G:174-176) or not processed (P:165)
+      if (nn == 0 && part == 0) {  // outside the coastal zone (G:174-176) or not processed (P:165)
         if (VARIANT == SBD_VARIANT_GENERIC) {
           a.sb[c] = a.prm.missing;
         } else {
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
           a.out[3 * n2 + c] = a.wd_in[c];             // P:280
         }
         if (a.flags) a.flags[c] = 0;
-      } else {
+      } else if (nn != 0) {
         const bool wide = nn > Rmax || nn > 56;
         b = (uint8_t)(((cd >> 15) << 7) | (wide ? 0x40u : (uint32_t)nn));
         if (!wide) rt = max(rt, nn);
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
     slot8[r] = -1; slot4[r][0] = slot4[r][1] = -1;
 #pragma unroll
     for (int q = 0; q < 8; ++q) slotc[r][q] = -1;
-    if (s8 < N8) {
+    if (s8 < N8 && (s8 % nparts) == part) {     // a split tile: this CTA owns every nparts-th 8-strip (and its cells)
       int kind8, kind4[2], nw8, nw4[2]; uint2 nb8;
       classify(s8, kind8, kind4, nw8, nw4, nb8);
       if (kind8) slot8[r] = atomicAdd(&s_c8[nw8], 1);
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
 #pragma unroll
   for (int r = 0; r < S8PT; ++r) {
     const int s8 = r * NT + tid;
-    if (s8 < N8) {
+    if (s8 < N8 && (s8 % nparts) == part) {
       int kind8, kind4[2], nw8, nw4[2]; uint2 nb8;
       classify(s8, kind8, kind4, nw8, nw4, nb8);
       const int sx = s8 / TY, sy = s8 % TY;

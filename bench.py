@@ -661,6 +661,12 @@ def bench_c3(ctx, args, steps, warmup, short=False):
     plan.set_timing(False)
     win = ctx.max_over_ranks(statistics.mean(win_ms))
     scn = ctx.max_over_ranks(statistics.mean(scan_ms))
+    win_all = [statistics.mean(win_ms)]
+    if world > 1:
+        wt = torch.tensor([statistics.mean(win_ms)], dtype=torch.float64, device=dev)
+        wl = [torch.zeros_like(wt) for _ in range(world)]
+        dist.all_gather(wl, wt)
+        win_all = [float(x.item()) for x in wl]
     ms_per_step = total_ms / steps
     value = n_cells * steps / (total_ms * 1e-3)
     n_coastal_all = int(ctx.sum_over_ranks(info["n_coastal"]))
@@ -752,7 +758,7 @@ def bench_c3(ctx, args, steps, warmup, short=False):
                 "frac": adds / (win * 1e-3) / (fp32_peak * world), "traffic": None,
                 "window_element_cells_per_step": elem_cells, "fp32_adds_per_step": adds,
                 "peak_source": "148 SMs x 128 FP32 lanes x 1.965 GHz (add rate measured with scripts/mb_pipes.cu: 94-96 % of it)",
-                "kernel_ms": win, "kernel_share_of_step": win / ms_per_step,
+                "kernel_ms": win, "kernel_ms_per_rank": win_all, "kernel_share_of_step": win / ms_per_step,
                 "hbm_algorithmic_bytes_per_step": abytes_step,
                 "hbm_step_frac": abytes_step / (ms_per_step * 1e-3) / 1e9 / (peak * world), "hbm_peak": peak, "hbm_peak_source": peak_src}
     cpu = None

@@ -290,6 +290,11 @@ int sbd_plan_set_peer_sync(sbd_plan* plan, uint32_t* sync_local, uint32_t* sync_
 int sbd_plan_set_window_kernel(sbd_plan* plan, int mode);
 /* Cells per strip of k_win8: 4 (default) or 8 (faster only where a tile's radii are nearly uniform). */
 int sbd_plan_set_strip_cells(sbd_plan* plan, int cells);
+/* k_win8 can give a tile whose window work exceeds a fair share of an SM's time to up to max_parts CTAs (each stages
+ * the tile and takes every max_parts-th strip); call before sbd_plan_set_static.  Default 1 = never split: measured on
+ * one eighth of the c3 grid (a rank's share at 8 GPUs) the window kernel takes 0.70 / 0.72 / 0.81 / 0.87 / 0.90 ms with
+ * 1 / 2 / 3 / 4 / 8 parts -- the duplicated staging and the thinner chunks cost more than the shorter tail saves. */
+int sbd_plan_set_tile_split(sbd_plan* plan, int max_parts);
 /* Process-wide: 1 = evaluate the sigmoid statistics with the plain sequential chain (one warp) instead of the exact
  * parallel formulation.  Same bits either way; kept as the in-library cross-check of the parallel form. */
 int sbd_set_stats_mode(int sequential);

@@ -35,6 +35,8 @@ if cfg.variant == "generic":
     for wk in modes:
         plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, nz, h)
         plan.set_window_kernel(wk)
+        if os.environ.get("PROBE_SPLIT"):
+            plan.set_tile_split(int(os.environ["PROBE_SPLIT"]))
         plan.set_static(mk, zh, sh)
         st = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(4)]
         for s in range(3):

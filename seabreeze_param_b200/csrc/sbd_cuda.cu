@@ -2117,6 +2117,7 @@ struct sbd_plan {
   int* d_tile_order = nullptr; // 64 x 32 tiles of the strip kernels, heaviest window work first (static)
   int* d_tile_split = nullptr; // k_win8: the same with heavy tiles given to several CTAs (tile | part << 20 | nparts << 26)
   int n_tile_split = 0;
+  int tile_split_max = 1;     // sbd_plan_set_tile_split: most CTAs one tile is given to (measured: splitting does not pay)
   int strip_cells = 4;        // sbd_plan_set_strip_cells: cells per strip of k_win8 (4 or 8)
   int window_kernel = 0;      // sbd_plan_set_window_kernel: 0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4)
   float* d_stats = nullptr;   // 4 floats
@@ -2706,6 +2707,13 @@ int sbd_plan_set_strip_cells(sbd_plan* p, int cells)
   p->strip_cells = cells;
   return SBD_OK;
 }
+int sbd_plan_set_tile_split(sbd_plan* p, int max_parts)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  if (max_parts < 1 || max_parts > 16) return fail(SBD_EINVAL, "tile split: 1..16 CTAs per tile");
+  p->tile_split_max = max_parts;
+  return SBD_OK;
+}
 int sbd_set_stats_mode(int sequential)
 {
   g_stats_seq.store(sequential ? 1 : 0);
@@ -2837,7 +2845,7 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
     const double share = std::max(total / (2.0 * nsm * 3.0), 2.0e5);
     std::vector<std::pair<float, int>> ents;
     for (int i = 0; i < nt; ++i) {
-      int np = (int)std::min(16.0, std::max(1.0, std::ceil(cost[i] / share)));
+      int np = (int)std::min((double)p->tile_split_max, std::max(1.0, std::ceil(cost[i] / share)));
       for (int k = 0; k < np; ++k) ents.push_back({cost[i] / np, (int)((uint32_t)i | ((uint32_t)k << 20) | ((uint32_t)np << 26))});
     }
     std::stable_sort(ents.begin(), ents.end(), [](const std::pair<float, int>& x, const std::pair<float, int>& y) { return x.first > y.first; });

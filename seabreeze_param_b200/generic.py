@@ -158,6 +158,10 @@ class Plan:
         """Cells per strip of the k_win8 window kernel: 4 (default) or 8.  See sbd_plan_set_strip_cells."""
         _capi.check(self.lib.sbd_plan_set_strip_cells(self._h, int(cells)), "plan_set_strip_cells")
 
+    def set_tile_split(self, max_parts):
+        """Most CTAs a heavy tile of the k_win8 window kernel is given to (before set_static).  See sbd_plan_set_tile_split."""
+        _capi.check(self.lib.sbd_plan_set_tile_split(self._h, int(max_parts)), "plan_set_tile_split")
+
     def window_info(self):
         """(nn, n_land, n_sea): int32 (ny, nx) arrays -- the radius at which the growing-window loop
         (G:188-214) stops for every cell and its land / sea counters; 0 outside the coastal zone."""

@@ -45,6 +45,8 @@ CONFIGS = {
                  "ERA-Interim-like 0.75 degree grid 480x241, 37 levels (python_wrapper/run.conf:5)"),
     "c3s": Config("c3s", 1000, 752, 4, 54, "generic", 40.0, True, 1440.0,
                   "probe: 1/16 of the regional 2.5 km domain (same mask statistics as c3), 4 levels"),
+    "c3r8": Config("c3r8", 4000, 384, 4, 54, "generic", 40.0, True, 1440.0,
+                   "probe: one of eight row blocks of the regional 2.5 km domain (a rank's share at 8 GPUs), 4 levels"),
     # small cases for unit tests
     "t_gen": Config("t_gen", 96, 64, 12, 5, "generic", 4.0, False, 1440.0, "test: small generic grid"),
     "t_py": Config("t_py", 360, 181, 9, 0, "python", 4.0, False, 360.0, "test: small python-variant grid"),

@@ -880,7 +880,10 @@ struct TrigArgs {
   // place instead of from a halo that somebody would have to fill first.
   const float* theta_up; const float* theta_dn;
   int ny_up;  // interior rows of the northern neighbour's block
-  int order;  // 0: scan -> window -> final (multi-GPU friendly); 1: window -> scan(+thresholds)
+  int order;  // 0: scan -> window -> final (multi-GPU friendly); 1: window -> scan(+thresholds);
+              // 2: scan(+thresholds) and window side by side, joined through join_ctr (small grids, see sbd_plan_step)
+  unsigned long long* join_ctr;    // order 2: window CTAs that have finished, counted over all steps of the plan
+  unsigned long long join_target;  // order 2: the count at which this step's window kernel is complete
   // Multi-GPU row blocks without a separate barrier launch: sync_local[0] / [1] are written by the
   // northern / southern neighbour rank ("my theta plane of step sync_seq is in place"); this rank
   // posts sync_seq into sync_up[1] and sync_dn[0].  Only CTAs that read neighbour rows wait.
@@ -902,6 +905,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns()
@@ -1451,6 +1460,11 @@ __global__ void __launch_bounds__(NT, (NT <= 256) ? (1536 / NT) : 1) k_trigger(c
       trigger_point<VARIANT>(a, c, n2, n_thc, n_ws, n_wd, 0.0f);
     }
   }
+  if (SPLIT && a.order == 2) {
+    // side-by-side step: the level scan's epilogue waits for this count instead of for the end of this grid
+    __syncthreads();
+    if (tid == 0) { __threadfence(); atomicAdd(a.join_ctr, 1ull); }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1928,7 +1942,7 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
   const int nz = a.nz;
   const float4* pq = reinterpret_cast<const float4*>(a.p) + m;
   // order 0: the window kernel follows as a dependent and may start now
-  if (a.order == 0) asm volatile("griddepcontrol.launch_dependents;");
+  if (a.order == 0 || a.order == 2) asm volatile("griddepcontrol.launch_dependents;");
   uint32_t cdq[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -1937,7 +1951,7 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
     cdq[j] = a.code[(size_t)(y + a.g.h) * a.g.ldx + (x + a.g.h)];
   }
   float4 ws4 = make_float4(0.f, 0.f, 0.f, 0.f), wd4 = ws4;
-  if (a.order == 1 && !a.first_step) {
+  if (a.order >= 1 && !a.first_step) {
     ws4 = __ldcg(reinterpret_cast<const float4*>(a.ws) + m);
     wd4 = __ldcg(reinterpret_cast<const float4*>(a.wd) + m);
   }
@@ -1992,10 +2006,20 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
   float nws[4], nwd[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) wind_from_uv(a, uu[j], vv[j], nws[j], nwd[j]);
-  if (a.order == 1) {
-    // this grid is the programmatic dependent of the window kernel: wait for its n_thc, then
-    // thresholds, scaling and state update right here (G:235-266) -- no further kernel
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (a.order >= 1) {
+    // order 1: this grid is the programmatic dependent of the window kernel: wait for its n_thc, then
+    // thresholds, scaling and state update right here (G:235-266) -- no further kernel.
+    // order 2: the window kernel runs BESIDE this grid (it is this grid's dependent and was released at entry);
+    // its CTAs count themselves into join_ctr, and by the time a scan thread gets here -- after streaming its
+    // pressure columns -- that count is normally complete already
+    if (a.order == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+    else {
+      const unsigned long long t0 = globaltimer_ns();
+      while (ld_acquire_gpu_u64(a.join_ctr) < a.join_target) {
+        __nanosleep(128);
+        if (globaltimer_ns() - t0 > 2000000000ull) { a.join_ctr[1] = a.join_target; break; }   // reported by sbd_plan_sync
+      }
+    }
     const float4 thc4 = __ldcg(reinterpret_cast<const float4*>(a.thc) + m);
     const float thc_[4] = {thc4.x, thc4.y, thc4.z, thc4.w};
     const float wsp[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
@@ -2114,6 +2138,9 @@ struct sbd_plan {
   uint16_t* d_code = nullptr;
   uint32_t* d_cl = nullptr;   // land cells in every coastal-zone cell's final window (k_static_counts)
   int row_lo = 0, row_hi = -1;  // sbd_plan_set_row_window (-1: to the end)
+  unsigned long long* d_join = nullptr;   // order-2 steps: finished window CTAs over all steps
+  unsigned long long join_count = 0;
+  bool side_by_side = false;  // the whole level scan fits beside the window kernel (decided in set_static)
   int* d_tile_order = nullptr; // 64 x 32 tiles of the strip kernels, heaviest window work first (static)
   int* d_tile_split = nullptr; // k_win8: the same with heavy tiles given to several CTAs (tile | part << 20 | nparts << 26)
   int n_tile_split = 0;
@@ -2379,7 +2406,7 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = (a.order == 0 && !p->timing) ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = ((a.order == 0 || a.order == 2) && !p->timing) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
@@ -2637,7 +2664,7 @@ void sbd_plan_destroy(sbd_plan* p)
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->e_copy) cudaEventDestroy(p->e_copy);
   if (p->e_main) cudaEventDestroy(p->e_main);
-  cudaFree(p->d_pfull); cudaFree(p->d_tile_order); cudaFree(p->d_tile_split);
+  cudaFree(p->d_pfull); cudaFree(p->d_join); cudaFree(p->d_tile_order); cudaFree(p->d_tile_split);
   for (int i = 0; i < 3; ++i) cudaFree(p->d_st_in[i]);
   cudaFree(p->d_sum);
   for (auto& s : p->stage) cudaFree(s.first);
@@ -2750,6 +2777,11 @@ void* sbd_plan_get_stream(sbd_plan* p) { return p ? (void*)p->stream : nullptr; 
 // neighbour rows that may not have been in place, so the step's results are not to be trusted
 static int check_peer_timeout(sbd_plan* p)
 {
+  if (p->d_join) {
+    unsigned long long mark = 0;
+    CK(cudaMemcpy(&mark, p->d_join + 1, sizeof mark, cudaMemcpyDeviceToHost));
+    if (mark) return fail(SBD_ECUDA, "internal: the level scan gave up waiting for the window kernel (side-by-side step)");
+  }
   if (!p->sync_local) return SBD_OK;
   uint32_t mark[2] = {0u, 0u};
   CK(cudaMemcpy(mark, p->sync_local + 2, sizeof mark, cudaMemcpyDeviceToHost));
@@ -2897,6 +2929,21 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
   if (p->variant == SBD_VARIANT_GENERIC && cnt[2] != cnt[1])
     return fail(SBD_ECUDA, "internal: compaction count differs from the coastal-cell count");
   p->R = (p->nn_max <= 16) ? p->nn_max : min(p->nn_max, 56);  // see launch_trigger
+  p->side_by_side = false;
+  if (p->variant == SBD_VARIANT_GENERIC && p->n_quads > 0) {
+    int occ = 0, nsm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan_quad_regs<5, 128>, 128, 0) == cudaSuccess) {
+      // every scan CTA resident in at most 60 % of the machine's slots: the rest is the window kernel's
+      p->side_by_side = (long long)cdiv(p->n_quads, 128) * 10 <= (long long)occ * nsm * 6;
+    } else cudaGetLastError();
+    if (p->side_by_side && !p->d_join) {
+      CK(cudaMalloc((void**)&p->d_join, 2 * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(p->d_join, 0, 2 * sizeof(unsigned long long), st));
+      p->join_count = 0;
+    }
+  }
   // split row of the hybrid host path
   p->ysplit = 0; p->n_quads_top = 0;
   if (p->variant == SBD_VARIANT_GENERIC && p->n_quads > 0) {
@@ -3073,6 +3120,23 @@ int sbd_plan_step(sbd_plan* p, float timestep, int step, const float* pp, const 
     // scalar scan / no coastal cells: scan -> window -> final, in order
     a.order = 0; p->last_order = 0;
     if ((rc = launch_scan(p, a))) return rc;
+    if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
+    return flush_out(p, pend, any_host);
+  }
+  // Small grids (N512 class): the whole level scan is resident at once and leaves room for the window kernel, so
+  // the two run SIDE BY SIDE from the first microsecond: scan first (ordinary launch, releases its dependent at
+  // entry), window kernel as its programmatic dependent, joined by a device counter that the scan's epilogue reads.
+  // With the window kernel first (order 1) its CTAs take the register file for the first ~10-25 us and the scan --
+  // the HBM-bound part that sets the step's floor -- starts late: c2 47 us per step against the scan's 36 us.
+  // Safe only when every scan CTA is resident (a waiting epilogue holds its SM slot): decided in set_static.
+  const int wmode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
+  const bool tile_kernel = (wmode == 1 && a.R <= 16) || (wmode == 0 && a.R < 9);   // launch_trigger picks k_trigger 64 x 16
+  if (p->side_by_side && !p->timing && tile_kernel && is_device_ptr(pp)) {
+    a.order = 2; p->last_order = 1;
+    const int n_win_ctas = cdiv(p->nx, 64) * cdiv(p->ny, 16);
+    p->join_count += (unsigned long long)n_win_ctas;
+    a.join_ctr = p->d_join; a.join_target = p->join_count;
+    if ((rc = launch_scan(p, a, false))) return rc;
     if ((rc = launch_trigger<SBD_VARIANT_GENERIC>(p, a))) return rc;
     return flush_out(p, pend, any_host);
   }

@@ -1,3 +1,3 @@
 #!/bin/bash
 cd ${GRAFT_REPO_ROOT:-.}; mkdir -p gpurun_out
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_step_quad -s 6 -c 1 -o gpurun_out/r2j_stepq python bench.py --no-cpu-baseline --no-e2e --steps 6 --warmup 3 > gpurun_out/r2j_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_win4 -s 4 -c 1 -o gpurun_out/r2p_win4_c4 python scripts/probe_win.py c4 2 > gpurun_out/r2p_ncu_c4.log 2>&1; echo "ncu c4 rc=$?"

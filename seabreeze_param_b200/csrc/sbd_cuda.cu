@@ -894,6 +894,7 @@ struct TrigArgs {
   // window work, heaviest first, so the light tiles fill the tail of the launch (CTAs are dispatched in order)
   const int* tile_order;
   int ntx;
+  int prefilled;  // python variant: k_py_fill has already written the output planes of cells outside the coastal zone
 };
 
 // ---- peer flags over NVLink (system scope) ----
@@ -1673,13 +1674,14 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
       if (nn == 0) {  // outside the coastal zone (G:174-176) or not processed (P:165)
         if (VARIANT == SBD_VARIANT_GENERIC) {
           a.sb[c] = a.prm.missing;
-        } else {
+          if (a.flags) a.flags[c] = 0;
+        } else if (!a.prefilled) {
           a.out[c] = a.prm.missing;                   // P:173
           a.out[n2 + c] = a.theta[so] - a.gzsm[so];   // P:278
           a.out[2 * n2 + c] = a.ws_in[c];             // P:279
           a.out[3 * n2 + c] = a.wd_in[c];             // P:280
+          if (a.flags) a.flags[c] = 0;
         }
-        if (a.flags) a.flags[c] = 0;
       } else {
         b = (uint8_t)(((cd >> 15) << 7) | ((nn > R || nn > 62) ? 0x40u : (uint32_t)nn));
       }
@@ -2037,6 +2039,54 @@ __global__ void __launch_bounds__(NT) k_scan_quad_regs(const TrigArgs a, const i
     for (int j = 0; j < 4; ++j)
       if (act[j]) { a.nws[c0 + j] = nws[j]; a.nwd[c0 + j] = nwd[j]; }
   }
+}
+
+// python variant, cells outside the coastal zone (and the never-processed last row, P:165): the four output planes
+// are pure data movement -- missing value, t0, and the incoming windspeed / winddir (P:173, P:277-280).  Done for
+// the strip window kernels as a streaming pass of its own (one thread per cell, coalesced), so that the window
+// kernel -- few resident CTAs, long-lived -- is left with the coastal-zone cells only.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_py_fill(const TrigArgs a)
+{
+  const size_t n2 = (size_t)a.g.nx * a.g.ny;
+  if (VEC) {
+    // four cells per thread, 16-byte accesses; a quad with coastal-zone cells falls through to the scalar stores
+    const size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m * 4 >= n2) return;
+    const uint2 cd = *reinterpret_cast<const uint2*>(a.code + m * 4);
+    const bool none = ((cd.x & 0x7fff7fffu) | (cd.y & 0x7fff7fffu)) == 0u;
+    if (none) {
+      const float4 th = __ldcs(reinterpret_cast<const float4*>(a.theta) + m);
+      const float4 gz = __ldg(reinterpret_cast<const float4*>(a.gzsm) + m);
+      const float ms = a.prm.missing;
+      __stcs(reinterpret_cast<float4*>(a.out) + m, make_float4(ms, ms, ms, ms));
+      __stcs(reinterpret_cast<float4*>(a.out + n2) + m, make_float4(th.x - gz.x, th.y - gz.y, th.z - gz.z, th.w - gz.w));
+      __stcs(reinterpret_cast<float4*>(a.out + 2 * n2) + m, __ldcs(reinterpret_cast<const float4*>(a.ws_in) + m));
+      __stcs(reinterpret_cast<float4*>(a.out + 3 * n2) + m, __ldcs(reinterpret_cast<const float4*>(a.wd_in) + m));
+      if (a.flags) reinterpret_cast<uint32_t*>(a.flags)[m] = 0u;
+      return;
+    }
+    const uint32_t c4[4] = {cd.x & 0x7fffu, (cd.x >> 16) & 0x7fffu, cd.y & 0x7fffu, (cd.y >> 16) & 0x7fffu};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t c = m * 4 + j;
+      if (c4[j] != 0u) continue;
+      a.out[c] = a.prm.missing;
+      a.out[n2 + c] = a.theta[c] - a.gzsm[c];
+      a.out[2 * n2 + c] = a.ws_in[c];
+      a.out[3 * n2 + c] = a.wd_in[c];
+      if (a.flags) a.flags[c] = 0;
+    }
+    return;
+  }
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n2) return;
+  if ((a.code[c] & 0x7fffu) != 0) return;        // coastal-zone cell: the window kernel writes all four planes
+  a.out[c] = a.prm.missing;                       // P:173
+  a.out[n2 + c] = a.theta[c] - a.gzsm[c];         // P:278
+  a.out[2 * n2 + c] = a.ws_in[c];                 // P:279
+  a.out[3 * n2 + c] = a.wd_in[c];                 // P:280
+  if (a.flags) a.flags[c] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3202,6 +3252,22 @@ int sbd_plan_step_py(sbd_plan* p, int step, float timestep_min, const float* pp,
   a.first_step = step < 2 ? 1 : 0;
   a.six_hourly = six_hourly_flag(step, timestep_min * 60.0f, p->prm.target_time);  // P:146, P:271
   a.prm = p->prm; a.gzsm = p->d_gzsm; a.code = p->d_code; a.cl = p->d_cl;
+  {
+    const int wmode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
+    const bool strips = (wmode == 2 || wmode == 3 || (wmode == 0 && a.R >= 9)) && a.R <= 56;
+    if (strips) {
+      const size_t n2c = (size_t)p->nx * p->ny;
+      if (p->timing) CK(cudaEventRecord(p->ev[2], p->stream));
+      auto al16 = [](const void* q) { return (((uintptr_t)q) & 15) == 0; };
+      const bool vec = (n2c % 4) == 0 && al16(a.theta) && al16(a.gzsm) && al16(a.ws_in) && al16(a.wd_in) && al16(a.out) &&
+                       (((uintptr_t)a.flags) & 3) == 0;
+      if (vec) k_py_fill<true><<<(unsigned)((n2c / 4 + 255) / 256), 256, 0, p->stream>>>(a);
+      else k_py_fill<false><<<(unsigned)((n2c + 255) / 256), 256, 0, p->stream>>>(a);
+      LAUNCHED();
+      if (p->timing) CK(cudaEventRecord(p->ev[3], p->stream));
+      a.prefilled = 1;
+    }
+  }
   if ((rc = launch_trigger<SBD_VARIANT_PYTHON>(p, a))) return rc;
   return flush_out(p, pend, any_host);
 }

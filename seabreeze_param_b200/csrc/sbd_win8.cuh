@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
       const uint32_t cd = a.code[so];
       const int nn = (int)(cd & 0x7fffu);
       const size_t c = (size_t)gy * a.g.nx + gx;
-      if (nn == 0 && part == 0) {  // outside the coastal zone (G:174-176) or not processed (P:165)
+      if (nn == 0 && part == 0 && !(VARIANT == SBD_VARIANT_PYTHON && a.prefilled)) {  // outside the coastal zone (G:174-176) or not processed (P:165)
         if (VARIANT == SBD_VARIANT_GENERIC) {
           a.sb[c] = a.prm.missing;
         } else {

@@ -57,6 +57,16 @@ __device__ __forceinline__ void add_pair_if(float& tl, float& ts, float vl, floa
       : "+f"(tl), "+f"(ts) : "f"(vl), "f"(vs), "r"(flag));
 }
 
+// Four consecutive steps of one cell under ONE predicate (a row that is inside / outside the cell's window).
+__device__ __forceinline__ void add4_if(float& tl, float& ts, float l0, float s0, float l1, float s1, float l2, float s2,
+                                        float l3, float s3, uint32_t flag)
+{
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %10, 0;\n\t"
+      "@q add.rn.f32 %0, %0, %2;\n\t@q add.rn.f32 %1, %1, %3;\n\t@q add.rn.f32 %0, %0, %4;\n\t@q add.rn.f32 %1, %1, %5;\n\t"
+      "@q add.rn.f32 %0, %0, %6;\n\t@q add.rn.f32 %1, %1, %7;\n\t@q add.rn.f32 %0, %0, %8;\n\t@q add.rn.f32 %1, %1, %9;\n\t}"
+      : "+f"(tl), "+f"(ts) : "f"(l0), "f"(s0), "f"(l1), "f"(s1), "f"(l2), "f"(s2), "f"(l3), "f"(s3), "r"(flag));
+}
+
 // bits k = 0..3 <-> steps base + k inside [lo, hi]
 __device__ __forceinline__ uint32_t range4(int lo, int hi, int base)
 {
@@ -83,6 +93,15 @@ __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP
   const int NIT_w = __reduce_max_sync(FULL, valid ? ((S + 3) >> 2) : 0);
   const int itL_w = __reduce_max_sync(FULL, valid ? ((sl + 3) >> 2) : 0);
   const int itR_w = __reduce_min_sync(FULL, itR);
+  // a row is walked in three phases with warp-uniform bounds that are multiples of NROT (so every phase starts
+  // with the register window un-rotated): [0, itA) switched per cell and step by the left masks, [itA, itB) every
+  // summing cell adds all four steps (rows beyond the smallest radius: switched per cell, once per row),
+  // [itB, NIT_w) switched by the right masks.  Keeping the three loops apart keeps the mask bookkeeping (shift
+  // counters per cell) out of the middle loop, which is where a wide window spends its time: integer adds cost
+  // more than an issue slot next to a saturated fma pipe (scripts/mb_mix.cu, profiles/r2_mb_mix.txt).
+  int itA = ((itL_w + NROT - 1) / NROT) * NROT;
+  int itB = (itR_w > itA) ? itA + ((itR_w - itA) / NROT) * NROT : itA;
+  if (itB <= itA || itA > 8) { itA = 0; itB = 0; }   // no unswitched part: the right-hand (general) masks all the way
   uint32_t ML[CW], MR[CW];
 #pragma unroll
   for (int q = 0; q < CW; ++q) {
@@ -91,8 +110,8 @@ __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP
       const int lo = off + nw - nq[q], hi = off + nw + nq[q];   // cell q's steps
       const int l1 = min(hi, 31);
       if (l1 >= lo) ml = (0xffffffffu >> (31 - (l1 - lo))) << lo;   // bit s, s < 32
-      const int r0 = max(lo - 4 * itR_w, 0), r1 = min(hi - 4 * itR_w, 31);
-      if (r1 >= r0) mr = (0xffffffffu >> (31 - (r1 - r0))) << r0;   // bit s - 4 itR_w
+      const int r0 = max(lo - 4 * itB, 0), r1 = min(hi - 4 * itB, 31);
+      if (r1 >= r0) mr = (0xffffffffu >> (31 - (r1 - r0))) << r0;   // bit s - 4 itB
     }
     ML[q] = ml; MR[q] = mr;
   }
@@ -102,9 +121,9 @@ __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP
     const float4* rp = reinterpret_cast<const float4*>(s_t + (size_t)(lrow + dy) * WP + lcol);
     const int ady = abs(dy);
     const bool core_row = ady <= nlo_w;      // warp-uniform
-    uint32_t PM[CW];                          // all ones where this row is inside cell q's window
+    uint32_t pr[CW];                          // this row is inside cell q's window
 #pragma unroll
-    for (int q = 0; q < CW; ++q) PM[q] = (ady <= nq[q] && nq[q] > 0) ? 0xffffffffu : 0u;
+    for (int q = 0; q < CW; ++q) pr[q] = (ady <= nq[q] && nq[q] > 0) ? 1u : 0u;
     // register window of NWIN = CW + 4 consecutive elements, each as (t_land, t_sea); the 16-byte load of the NEXT
     // iteration is issued before this iteration's adds and converted after them (shared-memory latency under the adds)
     float wl[NWIN], ws[NWIN];
@@ -119,53 +138,76 @@ __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP
         SBD_W_SET(8, g2.x) SBD_W_SET(9, g2.y) SBD_W_SET(10, g2.z) SBD_W_SET(11, g2.w)
       }
     }
-    auto body = [&](int it, auto rot) {
-      constexpr int ROT = decltype(rot)::value;           // logical window element i lives in slot (i + ROT) % NWIN
+    // logical window element i lives in slot (i + ROT) % NWIN; after the adds the four oldest elements are dead and
+    // their slots take the prefetched group
+#define SBD_W_ROTATE(gn) SBD_W_SET((0 + ROT) % NWIN, gn.x) SBD_W_SET((1 + ROT) % NWIN, gn.y) \
+                         SBD_W_SET((2 + ROT) % NWIN, gn.z) SBD_W_SET((3 + ROT) % NWIN, gn.w)
+    auto body_all = [&](int it, auto rot) {               // every summing cell, all four steps
+      constexpr int ROT = decltype(rot)::value;
       const float4 gn = rp[it + CW / 4 + 1];              // elements 4 it + CW + 4 .. + 7: the next iteration's
-      if (core_row && it >= itL_w && it < itR_w) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int q = 0; q < CW; ++q) {
-            accl[q] = __fadd_rn(accl[q], wl[(k + q + ROT) % NWIN]);   // G:200-202
-            accs[q] = __fadd_rn(accs[q], ws[(k + q + ROT) % NWIN]);   // G:204-205
-          }
-      } else {
-        uint32_t m[CW];
-        if (it >= itR_w) {
-          const int sh = 4 * (it - itR_w);
-          if (sh < 32) {
-#pragma unroll
-            for (int q = 0; q < CW; ++q) m[q] = (MR[q] >> sh) & PM[q];
-          } else {   // a warp that mixes very different radii: masks from the step ranges themselves
-#pragma unroll
-            for (int q = 0; q < CW; ++q)
-              m[q] = (valid && nq[q] > 0) ? (range4(off + nw - nq[q], off + nw + nq[q], 4 * it) & PM[q]) : 0u;
-          }
-        } else {
-          const int sh = 4 * it;                           // < 4 itR_w; beyond bit 31 every cell is active
-#pragma unroll
-          for (int q = 0; q < CW; ++q) m[q] = ((sh < 32) ? (ML[q] >> sh) : ((nq[q] > 0 && valid) ? 0xfu : 0u)) & PM[q];
+        for (int q = 0; q < CW; ++q) {
+          accl[q] = __fadd_rn(accl[q], wl[(k + q + ROT) % NWIN]);   // G:200-202
+          accs[q] = __fadd_rn(accs[q], ws[(k + q + ROT) % NWIN]);   // G:204-205
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int q = 0; q < CW; ++q)
-            add_pair_if(accl[q], accs[q], wl[(k + q + ROT) % NWIN], ws[(k + q + ROT) % NWIN], m[q] & (1u << k));
-      }
-      // the four oldest elements are dead now: their slots take the prefetched group
-      SBD_W_SET((0 + ROT) % NWIN, gn.x) SBD_W_SET((1 + ROT) % NWIN, gn.y)
-      SBD_W_SET((2 + ROT) % NWIN, gn.z) SBD_W_SET((3 + ROT) % NWIN, gn.w)
+      SBD_W_ROTATE(gn)
     };
-#undef SBD_W_SET
+    auto body_row = [&](int it, auto rot) {               // all four steps, cells switched by row
+      constexpr int ROT = decltype(rot)::value;
+      const float4 gn = rp[it + CW / 4 + 1];
+#pragma unroll
+      for (int q = 0; q < CW; ++q)
+        add4_if(accl[q], accs[q], wl[(q + ROT) % NWIN], ws[(q + ROT) % NWIN], wl[(1 + q + ROT) % NWIN], ws[(1 + q + ROT) % NWIN],
+                wl[(2 + q + ROT) % NWIN], ws[(2 + q + ROT) % NWIN], wl[(3 + q + ROT) % NWIN], ws[(3 + q + ROT) % NWIN], pr[q]);
+      SBD_W_ROTATE(gn)
+    };
+    auto body_mask = [&](int it, auto rot, auto mode) {   // switched per cell and step; mode 0 left, 1 right, 2 general
+      constexpr int ROT = decltype(rot)::value;
+      constexpr int MODE = decltype(mode)::value;
+      const float4 gn = rp[it + CW / 4 + 1];
+      uint32_t m[CW];
+      if (MODE == 0) {
+        const int sh = 4 * it;                            // < 4 itA <= 32
+#pragma unroll
+        for (int q = 0; q < CW; ++q) m[q] = pr[q] ? (ML[q] >> sh) : 0u;
+      } else if (MODE == 1) {
+        const int sh = 4 * (it - itB);                    // < 32: the caller's loop bound
+#pragma unroll
+        for (int q = 0; q < CW; ++q) m[q] = pr[q] ? (MR[q] >> sh) : 0u;
+      } else {                                            // masks from the step ranges themselves
+#pragma unroll
+        for (int q = 0; q < CW; ++q)
+          m[q] = (valid && pr[q]) ? range4(off + nw - nq[q], off + nw + nq[q], 4 * it) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < CW; ++q)
+          add_pair_if(accl[q], accs[q], wl[(k + q + ROT) % NWIN], ws[(k + q + ROT) % NWIN], m[q] & (1u << k));
+      SBD_W_ROTATE(gn)
+    };
+    // right-hand phase: full rounds of NROT through the shifted masks while the shift stays below 32, then the general form
+    const int itC = itB + min(NROT == 3 ? 6 : 8, ((NIT_w - itB) / NROT) * NROT);
     int it = 0;
     if (NROT == 3) {
-      for (; it + 3 <= NIT_w; it += 3) { body(it, IC<0>()); body(it + 1, IC<4>()); body(it + 2, IC<8>()); }
-      if (it < NIT_w) { body(it, IC<0>()); if (it + 1 < NIT_w) body(it + 1, IC<4>()); }
+      for (; it < itA; it += 3) { body_mask(it, IC<0>(), IC<0>()); body_mask(it + 1, IC<4>(), IC<0>()); body_mask(it + 2, IC<8>(), IC<0>()); }
+      if (core_row) for (; it < itB; it += 3) { body_all(it, IC<0>()); body_all(it + 1, IC<4>()); body_all(it + 2, IC<8>()); }
+      else          for (; it < itB; it += 3) { body_row(it, IC<0>()); body_row(it + 1, IC<4>()); body_row(it + 2, IC<8>()); }
+      for (; it < itC; it += 3) { body_mask(it, IC<0>(), IC<1>()); body_mask(it + 1, IC<4>(), IC<1>()); body_mask(it + 2, IC<8>(), IC<1>()); }
+      for (; it + 3 <= NIT_w; it += 3) { body_mask(it, IC<0>(), IC<2>()); body_mask(it + 1, IC<4>(), IC<2>()); body_mask(it + 2, IC<8>(), IC<2>()); }
+      if (it < NIT_w) { body_mask(it, IC<0>(), IC<2>()); if (it + 1 < NIT_w) body_mask(it + 1, IC<4>(), IC<2>()); }
     } else {
-      for (; it + 2 <= NIT_w; it += 2) { body(it, IC<0>()); body(it + 1, IC<4>()); }
-      if (it < NIT_w) body(it, IC<0>());
+      for (; it < itA; it += 2) { body_mask(it, IC<0>(), IC<0>()); body_mask(it + 1, IC<4>(), IC<0>()); }
+      if (core_row) for (; it < itB; it += 2) { body_all(it, IC<0>()); body_all(it + 1, IC<4>()); }
+      else          for (; it < itB; it += 2) { body_row(it, IC<0>()); body_row(it + 1, IC<4>()); }
+      for (; it < itC; it += 2) { body_mask(it, IC<0>(), IC<1>()); body_mask(it + 1, IC<4>(), IC<1>()); }
+      for (; it + 2 <= NIT_w; it += 2) { body_mask(it, IC<0>(), IC<2>()); body_mask(it + 1, IC<4>(), IC<2>()); }
+      if (it < NIT_w) body_mask(it, IC<0>(), IC<2>());
     }
+#undef SBD_W_ROTATE
+#undef SBD_W_SET
   }
 }
 

@@ -38,6 +38,22 @@ if cfg.variant == "generic":
         if os.environ.get("PROBE_SPLIT"):
             plan.set_tile_split(int(os.environ["PROBE_SPLIT"]))
         plan.set_static(mk, zh, sh)
+        if os.environ.get("PROBE_TILES"):
+            # how far from a perfectly divisible workload is this grid?  window elements per 64 x 32 tile, greedy
+            # heaviest-first assignment to 296 CTA slots (148 SMs x 2) against the mean load per slot
+            import heapq
+            nn = plan.window_info()[0].astype(np.float64)
+            el = (2 * nn + 1) ** 2 * (nn > 0)
+            ty, tx = (ny + 31) // 32, (nx + 63) // 64
+            pad = np.zeros((ty * 32, tx * 64)); pad[:ny, :nx] = el
+            tc = pad.reshape(ty, 32, tx, 64).sum(axis=(1, 3)).ravel()
+            tc = np.sort(tc[tc > 0])[::-1]
+            slots = [0.0] * 296
+            heapq.heapify(slots)
+            for c in tc:
+                heapq.heappush(slots, heapq.heappop(slots) + c)
+            print("   tiles with work %d, window elements %.4g, heaviest tile %.4g, mean per slot %.4g, greedy makespan %.4g (x%.2f of mean)"
+                  % (len(tc), tc.sum(), tc[0], tc.sum() / 296, max(slots), max(slots) / (tc.sum() / 296)))
         st = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(4)]
         for s in range(3):
             plan.step(cfg.timestep, s + 1, p, u, v, th, *st)

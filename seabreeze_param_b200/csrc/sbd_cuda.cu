@@ -4187,3 +4187,11 @@ int sbd_um_swap_bounds_f64(double* field, int row_len, int rows, int levels, int
 }
 
 }  // extern "C"
+
+#ifdef SBD_TRACE_TILES
+extern "C" int sbd_debug_tile_trace(unsigned long long* out, int n_ctas)
+{
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, sbdk::g_tile_trace, sizeof(unsigned long long) * 4 * (size_t)std::min(n_ctas, 16384));
+}
+#endif

@@ -57,6 +57,22 @@ __device__ __forceinline__ void add_pair_if(float& tl, float& ts, float vl, floa
       : "+f"(tl), "+f"(ts) : "f"(vl), "f"(vs), "r"(flag));
 }
 
+// One step of four cells, each under its own predicate (bit `bit` of its mask).  The four predicates are set first and
+// the eight adds follow: one predicate-latency bubble per step instead of one per cell (with a predicate per pair,
+// ptxas reuses a single predicate register and every pair waits ~13 cycles for it: 40 % of the kernel's samples).
+__device__ __forceinline__ void add_step4_if(float& l0, float& s0, float& l1, float& s1, float& l2, float& s2, float& l3, float& s3,
+                                             float a0, float b0, float a1, float b1, float a2, float b2, float a3, float b3,
+                                             uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t bit)
+{
+  asm("{\n\t.reg .pred pa, pb, pc, pd;\n\t.reg .b32 ta, tb, tc, td;\n\t"
+      "and.b32 ta, %16, %20;\n\tand.b32 tb, %17, %20;\n\tand.b32 tc, %18, %20;\n\tand.b32 td, %19, %20;\n\t"
+      "setp.ne.u32 pa, ta, 0;\n\tsetp.ne.u32 pb, tb, 0;\n\tsetp.ne.u32 pc, tc, 0;\n\tsetp.ne.u32 pd, td, 0;\n\t"
+      "@pa add.rn.f32 %0, %0, %8;\n\t@pa add.rn.f32 %1, %1, %9;\n\t@pb add.rn.f32 %2, %2, %10;\n\t@pb add.rn.f32 %3, %3, %11;\n\t"
+      "@pc add.rn.f32 %4, %4, %12;\n\t@pc add.rn.f32 %5, %5, %13;\n\t@pd add.rn.f32 %6, %6, %14;\n\t@pd add.rn.f32 %7, %7, %15;\n\t}"
+      : "+f"(l0), "+f"(s0), "+f"(l1), "+f"(s1), "+f"(l2), "+f"(s2), "+f"(l3), "+f"(s3)
+      : "f"(a0), "f"(b0), "f"(a1), "f"(b1), "f"(a2), "f"(b2), "f"(a3), "f"(b3), "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(bit));
+}
+
 // Four consecutive steps of one cell under ONE predicate (a row that is inside / outside the cell's window).
 __device__ __forceinline__ void add4_if(float& tl, float& ts, float l0, float s0, float l1, float s1, float l2, float s2,
                                         float l3, float s3, uint32_t flag)
@@ -123,7 +139,10 @@ __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP
     const bool core_row = ady <= nlo_w;      // warp-uniform
     uint32_t pr[CW];                          // this row is inside cell q's window
 #pragma unroll
-    for (int q = 0; q < CW; ++q) pr[q] = (ady <= nq[q] && nq[q] > 0) ? 1u : 0u;
+    for (int q = 0; q < CW; ++q) {              // integer masks, opaque to the compiler: it would turn `& pr` back into
+      pr[q] = (ady <= nq[q] && nq[q] > 0) ? 0xffffffffu : 0u;   // a select on a predicate held across the whole row,
+      asm volatile("" : "+r"(pr[q]));           // and predicates are what the switched loops are short of
+    }
     // register window of NWIN = CW + 4 consecutive elements, each as (t_land, t_sea); the 16-byte load of the NEXT
     // iteration is issued before this iteration's adds and converted after them (shared-memory latency under the adds)
     float wl[NWIN], ws[NWIN];
@@ -154,13 +173,14 @@ __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP
         }
       SBD_W_ROTATE(gn)
     };
+    uint32_t prc[CW];                                     // pr[] again, defined just before the middle loop (below)
     auto body_row = [&](int it, auto rot) {               // all four steps, cells switched by row
       constexpr int ROT = decltype(rot)::value;
       const float4 gn = rp[it + CW / 4 + 1];
 #pragma unroll
       for (int q = 0; q < CW; ++q)
         add4_if(accl[q], accs[q], wl[(q + ROT) % NWIN], ws[(q + ROT) % NWIN], wl[(1 + q + ROT) % NWIN], ws[(1 + q + ROT) % NWIN],
-                wl[(2 + q + ROT) % NWIN], ws[(2 + q + ROT) % NWIN], wl[(3 + q + ROT) % NWIN], ws[(3 + q + ROT) % NWIN], pr[q]);
+                wl[(2 + q + ROT) % NWIN], ws[(2 + q + ROT) % NWIN], wl[(3 + q + ROT) % NWIN], ws[(3 + q + ROT) % NWIN], prc[q]);
       SBD_W_ROTATE(gn)
     };
     auto body_mask = [&](int it, auto rot, auto mode) {   // switched per cell and step; mode 0 left, 1 right, 2 general
@@ -171,41 +191,48 @@ __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP
       if (MODE == 0) {
         const int sh = 4 * it;                            // < 4 itA <= 32
 #pragma unroll
-        for (int q = 0; q < CW; ++q) m[q] = pr[q] ? (ML[q] >> sh) : 0u;
+        for (int q = 0; q < CW; ++q) m[q] = (ML[q] >> sh) & pr[q];
       } else if (MODE == 1) {
         const int sh = 4 * (it - itB);                    // < 32: the caller's loop bound
 #pragma unroll
-        for (int q = 0; q < CW; ++q) m[q] = pr[q] ? (MR[q] >> sh) : 0u;
+        for (int q = 0; q < CW; ++q) m[q] = (MR[q] >> sh) & pr[q];
       } else {                                            // masks from the step ranges themselves
 #pragma unroll
         for (int q = 0; q < CW; ++q)
-          m[q] = (valid && pr[q]) ? range4(off + nw - nq[q], off + nw + nq[q], 4 * it) : 0u;
+          m[q] = valid ? (range4(off + nw - nq[q], off + nw + nq[q], 4 * it) & pr[q]) : 0u;
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int q = 0; q < CW; ++q)
-          add_pair_if(accl[q], accs[q], wl[(k + q + ROT) % NWIN], ws[(k + q + ROT) % NWIN], m[q] & (1u << k));
+        for (int q = 0; q < CW; q += 4)
+          add_step4_if(accl[q], accs[q], accl[q + 1], accs[q + 1], accl[q + 2], accs[q + 2], accl[q + 3], accs[q + 3],
+                       wl[(k + q + ROT) % NWIN], ws[(k + q + ROT) % NWIN], wl[(k + q + 1 + ROT) % NWIN], ws[(k + q + 1 + ROT) % NWIN],
+                       wl[(k + q + 2 + ROT) % NWIN], ws[(k + q + 2 + ROT) % NWIN], wl[(k + q + 3 + ROT) % NWIN], ws[(k + q + 3 + ROT) % NWIN],
+                       m[q], m[q + 1], m[q + 2], m[q + 3], 1u << k);
       SBD_W_ROTATE(gn)
     };
     // right-hand phase: full rounds of NROT through the shifted masks while the shift stays below 32, then the general form
     const int itC = itB + min(NROT == 3 ? 6 : 8, ((NIT_w - itB) / NROT) * NROT);
+    // the row predicates of the middle loop must not be set before the left-hand loop: ptxas would hoist them to the
+    // top of the row and the switched loops, left with one free predicate, would wait for it at every pair of adds
+#define SBD_PRC_DEFINE _Pragma("unroll") for (int q = 0; q < CW; ++q) { prc[q] = pr[q]; asm volatile("" : "+r"(prc[q])); }
     int it = 0;
     if (NROT == 3) {
       for (; it < itA; it += 3) { body_mask(it, IC<0>(), IC<0>()); body_mask(it + 1, IC<4>(), IC<0>()); body_mask(it + 2, IC<8>(), IC<0>()); }
       if (core_row) for (; it < itB; it += 3) { body_all(it, IC<0>()); body_all(it + 1, IC<4>()); body_all(it + 2, IC<8>()); }
-      else          for (; it < itB; it += 3) { body_row(it, IC<0>()); body_row(it + 1, IC<4>()); body_row(it + 2, IC<8>()); }
+      else { SBD_PRC_DEFINE for (; it < itB; it += 3) { body_row(it, IC<0>()); body_row(it + 1, IC<4>()); body_row(it + 2, IC<8>()); } }
       for (; it < itC; it += 3) { body_mask(it, IC<0>(), IC<1>()); body_mask(it + 1, IC<4>(), IC<1>()); body_mask(it + 2, IC<8>(), IC<1>()); }
       for (; it + 3 <= NIT_w; it += 3) { body_mask(it, IC<0>(), IC<2>()); body_mask(it + 1, IC<4>(), IC<2>()); body_mask(it + 2, IC<8>(), IC<2>()); }
       if (it < NIT_w) { body_mask(it, IC<0>(), IC<2>()); if (it + 1 < NIT_w) body_mask(it + 1, IC<4>(), IC<2>()); }
     } else {
       for (; it < itA; it += 2) { body_mask(it, IC<0>(), IC<0>()); body_mask(it + 1, IC<4>(), IC<0>()); }
       if (core_row) for (; it < itB; it += 2) { body_all(it, IC<0>()); body_all(it + 1, IC<4>()); }
-      else          for (; it < itB; it += 2) { body_row(it, IC<0>()); body_row(it + 1, IC<4>()); }
+      else { SBD_PRC_DEFINE for (; it < itB; it += 2) { body_row(it, IC<0>()); body_row(it + 1, IC<4>()); } }
       for (; it < itC; it += 2) { body_mask(it, IC<0>(), IC<1>()); body_mask(it + 1, IC<4>(), IC<1>()); }
       for (; it + 2 <= NIT_w; it += 2) { body_mask(it, IC<0>(), IC<2>()); body_mask(it + 1, IC<4>(), IC<2>()); }
       if (it < NIT_w) body_mask(it, IC<0>(), IC<2>());
     }
+#undef SBD_PRC_DEFINE
 #undef SBD_W_ROTATE
 #undef SBD_W_SET
   }
@@ -226,9 +253,18 @@ __device__ __forceinline__ unsigned long long window_fixed_sc(const float* __res
   return acc;
 }
 
+#ifdef SBD_TRACE_TILES
+// diagnostic build only (-DSBD_TRACE_TILES, scripts/probe_tiles.py): per CTA {launch entry, SM, start ns, end ns}
+__device__ unsigned long long g_tile_trace[4 * 16384];
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <int VARIANT, bool SPLIT, int NT, bool USE8>
 __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
 {
+#ifdef SBD_TRACE_TILES
+  const unsigned long long tr_t0 = trace_now();
+#endif
   constexpr int TX = 64, TY = 32, NW = NT / 32;
   constexpr int N8 = TX * TY / 8, N4 = TX * TY / 4, NC = TX * TY;
   constexpr int NB = 64;        // radius buckets (radii <= 56 inside the tile)
@@ -582,4 +618,12 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
       }
     }
   }
+#ifdef SBD_TRACE_TILES
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < 16384) {
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_tile_trace[4 * blockIdx.x + 0] = ent; g_tile_trace[4 * blockIdx.x + 1] = smid;
+    g_tile_trace[4 * blockIdx.x + 2] = tr_t0; g_tile_trace[4 * blockIdx.x + 3] = trace_now();
+  }
+#endif
 }

@@ -295,6 +295,10 @@ int sbd_plan_set_strip_cells(sbd_plan* plan, int cells);
  * one eighth of the c3 grid (a rank's share at 8 GPUs) the window kernel takes 0.70 / 0.72 / 0.81 / 0.87 / 0.90 ms with
  * 1 / 2 / 3 / 4 / 8 parts -- the duplicated staging and the thinner chunks cost more than the shorter tail saves. */
 int sbd_plan_set_tile_split(sbd_plan* plan, int max_parts);
+/* Rows per tile of k_win8: 32 (default, also what 0 = auto resolves to) or 16.  Half-height tiles halve the longest
+ * CTA of a launch but were measured slower on every grid tried (a 4000 x 384 block of c3: 0.59 ms against 0.48 ms);
+ * kept for experiments. */
+int sbd_plan_set_tile_rows(sbd_plan* plan, int rows);
 /* Process-wide: 1 = evaluate the sigmoid statistics with the plain sequential chain (one warp) instead of the exact
  * parallel formulation.  Same bits either way; kept as the in-library cross-check of the parallel form. */
 int sbd_set_stats_mode(int sequential);

@@ -35,12 +35,17 @@ def haloed(a2d):
     generic.swap_bounds(f, h); return f
 mk, zh, sh, th = haloed(cdist), haloed(t(z)), haloed(t(sig)), haloed(theta)
 plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, nz, h)
-plan.set_window_kernel(3); plan.set_tile_split(split); plan.set_static(mk, zh, sh)
+plan.set_window_kernel(3); plan.set_tile_split(split)
+if os.environ.get("PROBE_ROWS"):
+    plan.set_tile_rows(int(os.environ["PROBE_ROWS"]))
+plan.set_static(mk, zh, sh)
 nn = plan.window_info()[0].astype(np.float64)
 el = (2 * nn + 1) ** 2 * (nn > 0)
-ty, tx = (ny + 31) // 32, (nx + 63) // 64
-pad = np.zeros((ty * 32, tx * 64)); pad[:ny, :nx] = el
-tcost = pad.reshape(ty, 32, tx, 64).sum(axis=(1, 3)).ravel()
+TR = int(os.environ.get("PROBE_ROWS", "32"))
+plan.set_tile_rows(TR)              # (again: explicit even without the variable, so the cost map matches the launch)
+ty, tx = (ny + TR - 1) // TR, (nx + 63) // 64
+pad = np.zeros((ty * TR, tx * 64)); pad[:ny, :nx] = el
+tcost = pad.reshape(ty, TR, tx, 64).sum(axis=(1, 3)).ravel()
 st = [torch.zeros((ny, nx), dtype=torch.float32, device=dev) for _ in range(4)]
 for s in range(4):
     plan.step(cfg.timestep, s + 1, p, u, v, th, *st)
@@ -56,7 +61,7 @@ tile, part, nparts = ent & 0xfffff, (ent >> 20) & 0x3f, ent >> 26
 T0 = t0.min(); t0 = (t0 - T0) / 1e3; t1 = (t1 - T0) / 1e3
 dur = t1 - t0
 cost = tcost[tile] / np.maximum(nparts, 1)
-print("%s split %d: %d CTAs, kernel span %.0f us, sum of CTA time %.0f us = %.1f slots busy on average (of 296)"
+print("rows per tile %d;" % TR, "%s split %d: %d CTAs, kernel span %.0f us, sum of CTA time %.0f us = %.1f slots busy on average (of 296)"
       % (name, split, len(buf), t1.max(), dur.sum(), dur.sum() / t1.max()))
 o = np.argsort(-dur)
 print("longest CTAs: dur us / start us / window elements / elements per us / sm")

@@ -37,6 +37,8 @@ if cfg.variant == "generic":
         plan.set_window_kernel(wk)
         if os.environ.get("PROBE_SPLIT"):
             plan.set_tile_split(int(os.environ["PROBE_SPLIT"]))
+        if os.environ.get("PROBE_ROWS"):
+            plan.set_tile_rows(int(os.environ["PROBE_ROWS"]))
         plan.set_static(mk, zh, sh)
         if os.environ.get("PROBE_TILES"):
             # how far from a perfectly divisible workload is this grid?  window elements per 64 x 32 tile, greedy

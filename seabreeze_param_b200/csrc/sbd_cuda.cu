@@ -803,12 +803,12 @@ __global__ void k_static_code(const float* __restrict__ mask, uint16_t* __restri
   code[s] = (uint16_t)c;
 }
 
-// window work of every 64 x 32 tile of the strip kernels: sum of (2nn+1)^2 over its coastal-zone cells (+ a
+// window work of every 64 x TY tile of the strip kernels: sum of (2nn+1)^2 over its coastal-zone cells (+ a
 // constant per cell for staging and the pointwise part); one CTA per tile
 template <int VARIANT>
-__global__ void __launch_bounds__(256) k_tile_cost(const uint16_t* __restrict__ code, Geo g, int ntx, float* __restrict__ cost)
+__global__ void __launch_bounds__(256) k_tile_cost(const uint16_t* __restrict__ code, Geo g, int ntx, int TY, float* __restrict__ cost)
 {
-  constexpr int TX = 64, TY = 32;
+  constexpr int TX = 64;
   const int tile = blockIdx.x, tx = tile % ntx, ty = tile / ntx;
   float acc = 0.0f;
   for (int t = threadIdx.x; t < TX * TY; t += blockDim.x) {
@@ -2194,6 +2194,10 @@ struct sbd_plan {
   int* d_tile_order = nullptr; // 64 x 32 tiles of the strip kernels, heaviest window work first (static)
   int* d_tile_split = nullptr; // k_win8: the same with heavy tiles given to several CTAs (tile | part << 20 | nparts << 26)
   int n_tile_split = 0;
+  int* d_tile_split16 = nullptr;  // k_win8 with 64 x 16 tiles
+  int n_tile_split16 = 0;
+  int tile_rows = 0;          // sbd_plan_set_tile_rows: 0 auto, 16, 32
+  int tile_rows_auto = 32;    // what auto resolves to for this plan's radius plane (set_static)
   int tile_split_max = 1;     // sbd_plan_set_tile_split: most CTAs one tile is given to (measured: splitting does not pay)
   int strip_cells = 4;        // sbd_plan_set_strip_cells: cells per strip of k_win8 (4 or 8)
   int window_kernel = 0;      // sbd_plan_set_window_kernel: 0 auto, 1 tile kernel (k_trigger), 2 strip kernel (k_win4)
@@ -2522,19 +2526,19 @@ int launch_win4(sbd_plan* p, TrigArgs& a)
 }
 
 // strip form of the window kernel, round 2 (k_win8, sbd_win8.cuh): tile 64 x 32, one float per staged cell
-template <int VARIANT, int NT, bool USE8>
+template <int VARIANT, int NT, bool USE8, int TY>
 int launch_win8_cfg(sbd_plan* p, TrigArgs& a)
 {
   constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
-  constexpr int TX = 64, TY = 32;
+  constexpr int TX = 64;
   const int R = a.R;
   const int WPmax = ((TX + 2 * R + 3) & ~3) + 4;
   const size_t smem = (size_t)WPmax * (TY + 2 * R) * 4 + TX * TY + (size_t)(TX * TY / 8 + TX * TY / 4 + TX * TY) * 2;
-  auto kern = k_win8<VARIANT, GEN, NT, USE8>;
+  auto kern = k_win8<VARIANT, GEN, NT, USE8, TY>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   a.ntx = cdiv(p->nx, TX);
-  a.tile_order = p->d_tile_split;
-  dim3 grid(p->n_tile_split);
+  a.tile_order = TY == 16 ? p->d_tile_split16 : p->d_tile_split;
+  dim3 grid(TY == 16 ? p->n_tile_split16 : p->n_tile_split);
   a.nws = p->d_nws;
   a.nwd = p->d_nwd;
   cudaLaunchConfig_t cfg = {};
@@ -2569,8 +2573,10 @@ int launch_win8(sbd_plan* p, TrigArgs& a)
   // strips where the radius allows 6.2 ms -- a tile then has only 8 chunks and the longest one sets its time
   // (sbd_plan_set_strip_cells(8) selects that form; it is the better one only for tiles of near-uniform radius).
   a.strip_min = 0;
-  if (p->strip_cells == 8) return launch_win8_cfg<VARIANT, 256, true>(p, a);
-  return launch_win8_cfg<VARIANT, 256, false>(p, a);
+  if (p->strip_cells == 8) return launch_win8_cfg<VARIANT, 256, true, 32>(p, a);
+  // 64 x 16 tiles only on request (sbd_plan_set_tile_rows): measured slower, see set_static
+  if ((p->tile_rows ? p->tile_rows : p->tile_rows_auto) == 16) return launch_win8_cfg<VARIANT, 256, false, 16>(p, a);
+  return launch_win8_cfg<VARIANT, 256, false, 32>(p, a);
 }
 
 template <int VARIANT>
@@ -2714,7 +2720,7 @@ void sbd_plan_destroy(sbd_plan* p)
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->e_copy) cudaEventDestroy(p->e_copy);
   if (p->e_main) cudaEventDestroy(p->e_main);
-  cudaFree(p->d_pfull); cudaFree(p->d_join); cudaFree(p->d_tile_order); cudaFree(p->d_tile_split);
+  cudaFree(p->d_pfull); cudaFree(p->d_join); cudaFree(p->d_tile_order); cudaFree(p->d_tile_split); cudaFree(p->d_tile_split16);
   for (int i = 0; i < 3; ++i) cudaFree(p->d_st_in[i]);
   cudaFree(p->d_sum);
   for (auto& s : p->stage) cudaFree(s.first);
@@ -2789,6 +2795,13 @@ int sbd_plan_set_tile_split(sbd_plan* p, int max_parts)
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
   if (max_parts < 1 || max_parts > 16) return fail(SBD_EINVAL, "tile split: 1..16 CTAs per tile");
   p->tile_split_max = max_parts;
+  return SBD_OK;
+}
+int sbd_plan_set_tile_rows(sbd_plan* p, int rows)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  if (rows != 0 && rows != 16 && rows != 32) return fail(SBD_EINVAL, "tile rows: 0 (auto), 16 or 32");
+  p->tile_rows = rows;
   return SBD_OK;
 }
 int sbd_set_stats_mode(int sequential)
@@ -2899,16 +2912,47 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
   CK(cudaGetLastError());
   {
     // launch order of the strip kernels' tiles: by window work, heaviest first
-    const int ntx = cdiv(p->nx, 64), nty = cdiv(p->ny, 32), nt = ntx * nty;
-    float* d_cost = nullptr;
-    CK(cudaMallocAsync((void**)&d_cost, sizeof(float) * nt, st));
-    if (p->variant == SBD_VARIANT_GENERIC) k_tile_cost<SBD_VARIANT_GENERIC><<<nt, 256, 0, st>>>(p->d_code, p->g, ntx, d_cost);
-    else k_tile_cost<SBD_VARIANT_PYTHON><<<nt, 256, 0, st>>>(p->d_code, p->g, ntx, d_cost);
-    LAUNCHED();
-    std::vector<float> cost(nt);
-    CK(cudaMemcpyAsync(cost.data(), d_cost, sizeof(float) * nt, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaFreeAsync(d_cost, st));
+    int nsm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+    auto tile_costs = [&](int TY, std::vector<float>& cost) -> int {
+      const int ntx = cdiv(p->nx, 64), nty = cdiv(p->ny, TY), nt = ntx * nty;
+      float* d_cost = nullptr;
+      CK(cudaMallocAsync((void**)&d_cost, sizeof(float) * nt, st));
+      if (p->variant == SBD_VARIANT_GENERIC) k_tile_cost<SBD_VARIANT_GENERIC><<<nt, 256, 0, st>>>(p->d_code, p->g, ntx, TY, d_cost);
+      else k_tile_cost<SBD_VARIANT_PYTHON><<<nt, 256, 0, st>>>(p->d_code, p->g, ntx, TY, d_cost);
+      LAUNCHED();
+      cost.resize(nt);
+      CK(cudaMemcpyAsync(cost.data(), d_cost, sizeof(float) * nt, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaFreeAsync(d_cost, st));
+      return SBD_OK;
+    };
+    // k_win8: a tile's CTA lives as long as its window sums take (a 64 x 32 tile of radius 50 is 2e7 window
+    // elements: ~0.5 ms of half an SM), which bounds the launch from below however many GPUs share the grid.
+    // sbd_plan_set_tile_split: tiles heavier than a third of a CTA slot's fair share are given to several CTAs (each
+    // stages the tile and takes every nparts-th 8-cell strip); entries sorted by work per CTA, heaviest first.
+    auto split_list = [&](const std::vector<float>& cost, int** d_list, int* n_list) -> int {
+      double total = 0.0;
+      for (float c : cost) total += c;
+      const double share = std::max(total / (2.0 * nsm * 3.0), 2.0e5);
+      std::vector<std::pair<float, int>> ents;
+      for (int i = 0; i < (int)cost.size(); ++i) {
+        int np = (int)std::min((double)p->tile_split_max, std::max(1.0, std::ceil(cost[i] / share)));
+        for (int k = 0; k < np; ++k) ents.push_back({cost[i] / np, (int)((uint32_t)i | ((uint32_t)k << 20) | ((uint32_t)np << 26))});
+      }
+      std::stable_sort(ents.begin(), ents.end(), [](const std::pair<float, int>& x, const std::pair<float, int>& y) { return x.first > y.first; });
+      std::vector<int> split(ents.size());
+      for (size_t i = 0; i < ents.size(); ++i) split[i] = ents[i].second;
+      CK(cudaFree(*d_list));
+      *d_list = nullptr;
+      *n_list = (int)split.size();
+      CK(cudaMalloc((void**)d_list, sizeof(int) * split.size()));
+      CK(cudaMemcpyAsync(*d_list, split.data(), sizeof(int) * split.size(), cudaMemcpyHostToDevice, st));
+      return SBD_OK;
+    };
+    std::vector<float> cost;
+    { int rc = tile_costs(32, cost); if (rc != SBD_OK) return rc; }
+    const int nt = (int)cost.size();
     std::vector<int> order(nt);
     for (int i = 0; i < nt; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
@@ -2916,28 +2960,14 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
     p->d_tile_order = nullptr;
     CK(cudaMalloc((void**)&p->d_tile_order, sizeof(int) * nt));
     CK(cudaMemcpyAsync(p->d_tile_order, order.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, st));
-    // k_win8: a tile's CTA lives as long as its window sums take (a 64 x 32 tile of radius 50 is 2e7 window
-    // elements: ~0.7 ms of one SM), which bounds the launch from below however many GPUs share the grid.  Tiles
-    // heavier than a third of a CTA slot's fair share are therefore given to several CTAs (each stages the tile
-    // and takes every nparts-th 8-cell strip); entries sorted by work per CTA, heaviest first.
-    double total = 0.0;
-    for (float c : cost) total += c;
-    int nsm = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-    const double share = std::max(total / (2.0 * nsm * 3.0), 2.0e5);
-    std::vector<std::pair<float, int>> ents;
-    for (int i = 0; i < nt; ++i) {
-      int np = (int)std::min((double)p->tile_split_max, std::max(1.0, std::ceil(cost[i] / share)));
-      for (int k = 0; k < np; ++k) ents.push_back({cost[i] / np, (int)((uint32_t)i | ((uint32_t)k << 20) | ((uint32_t)np << 26))});
-    }
-    std::stable_sort(ents.begin(), ents.end(), [](const std::pair<float, int>& x, const std::pair<float, int>& y) { return x.first > y.first; });
-    std::vector<int> split(ents.size());
-    for (size_t i = 0; i < ents.size(); ++i) split[i] = ents[i].second;
-    CK(cudaFree(p->d_tile_split));
-    p->d_tile_split = nullptr;
-    p->n_tile_split = (int)split.size();
-    CK(cudaMalloc((void**)&p->d_tile_split, sizeof(int) * split.size()));
-    CK(cudaMemcpyAsync(p->d_tile_split, split.data(), sizeof(int) * split.size(), cudaMemcpyHostToDevice, st));
+    { int rc = split_list(cost, &p->d_tile_split, &p->n_tile_split); if (rc != SBD_OK) return rc; }
+    // 64 x 16 tiles (sbd_plan_set_tile_rows(16)) halve the longest CTA; measured on a 4000 x 384 block of c3, where
+    // the heaviest 64 x 32 tile is 2.2x the mean load of a CTA slot: window kernel 0.48 ms with 32 rows, 0.59 ms with
+    // 16 (sum of CTA lifetimes 107 -> 146 ms: 8 chunks for 8 warps leave nothing to balance inside the tile, and the
+    // halo is staged twice as often).  Auto therefore always resolves to 32.
+    p->tile_rows_auto = 32;
+    { int rc = tile_costs(16, cost); if (rc != SBD_OK) return rc; }
+    { int rc = split_list(cost, &p->d_tile_split16, &p->n_tile_split16); if (rc != SBD_OK) return rc; }
     CK(cudaStreamSynchronize(st));
   }
   if (p->variant == SBD_VARIANT_GENERIC) {

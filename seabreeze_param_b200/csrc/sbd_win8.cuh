@@ -25,7 +25,7 @@
 //   * the tile's halo is the largest radius that actually occurs in the tile, not the plan-wide maximum.
 //   * work items (8-strips, 4-strips, single cells) are bucketed by radius, longest first, and handed to
 //     warps in chunks of 32 through a shared counter.
-// Tile 64 x 32 cells, 256 threads.
+// Tile 64 x 32 (or 64 x 16) cells, 256 threads.
 
 __device__ __forceinline__ unsigned long long mkpair(float x)
 {
@@ -259,16 +259,21 @@ __device__ unsigned long long g_tile_trace[4 * 16384];
 __device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-template <int VARIANT, bool SPLIT, int NT, bool USE8>
+template <int VARIANT, bool SPLIT, int NT, bool USE8, int TYV>
 __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
 {
 #ifdef SBD_TRACE_TILES
   const unsigned long long tr_t0 = trace_now();
 #endif
-  constexpr int TX = 64, TY = 32, NW = NT / 32;
+  // TYV = 32 rows per tile; 16 (sbd_plan_set_tile_rows) halves the longest CTA of a launch, but a 64 x 16 tile has 8
+  // chunks of strips for its 8 warps -- nothing to balance a long chunk against -- and stages 1.7x as much per cell:
+  // measured slower everywhere (profiles/r2_probe_tiles.txt), kept as a knob
+  constexpr int TX = 64, TY = TYV, NW = NT / 32;
   constexpr int N8 = TX * TY / 8, N4 = TX * TY / 4, NC = TX * TY;
   constexpr int NB = 64;        // radius buckets (radii <= 56 inside the tile)
   constexpr int MIN4 = 6;
+  constexpr int LONE4 = 24;     // a lone coastal-zone cell of at least this radius is walked as a strip
+  constexpr int CFIRST = 32;    // single cells of at least this radius (and the global-path ones) are handed out before the strips
   const int MIN8 = !USE8 ? (1 << 20) : (a.strip_min > 0 ? a.strip_min : 12);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Rmax = a.R;         // the launch's shared-memory size covers a halo of Rmax
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
   uint16_t* s_i4 = s_i8 + N8;                                 // 4-strip ids
   uint16_t* s_ic = s_i4 + N4;                                 // cell ids
   __shared__ int s_c8[NB], s_c4[NB], s_cc[NB], s_o8[NB], s_o4[NB], s_oc[NB];
-  __shared__ int s_lev, s_n8, s_n4, s_nc, s_rt, s_bad, s_next;
+  __shared__ int s_lev, s_n8, s_n4, s_nc, s_ncw, s_rt, s_bad, s_next;
 
   // launch entry: tile id | part << 20 | nparts << 26.  Heaviest tiles first; a tile whose window work exceeds a fair
   // share of an SM's time is given to `nparts` CTAs, each of which stages the tile and takes every nparts-th chunk
@@ -417,7 +422,10 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
         const int nn = (b & 0x40u) ? 0 : (int)(b & 0x3fu);
         if (nn > 0) { nw4[hlf] = max(nw4[hlf], nn); lo4 = min(lo4, nn); ++n4c; }
       }
-      if (n4c >= 2 && nw4[hlf] >= MIN4 && nw4[hlf] - lo4 <= 3) kind4[hlf] = 1;
+      // (a lone coastal-zone cell of a wide radius -- the rim of the zone, where radii are largest -- still goes through
+      //  the strip walk: as a single cell it would run the scalar loop, ~60 us for radius 54, at the very end of the
+      //  tile with one warp alive)
+      if ((n4c >= 2 || nw4[hlf] >= LONE4) && nw4[hlf] >= MIN4 && nw4[hlf] - lo4 <= 3) kind4[hlf] = 1;
       nw8 = max(nw8, nw4[hlf]); lo8 = min(lo8, lo4); n8c += n4c;
     }
     if (USE8 && n8c >= 2 && nw8 >= MIN8 && nw8 - lo8 <= 7) { kind8 = 1; kind4[0] = kind4[1] = 0; }
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
       int* off = lane == 0 ? s_o8 : (lane == 1 ? s_o4 : s_oc);
       int run = 0;
       for (int k = NB - 1; k >= 0; --k) { off[k] = run; run += cnt[k]; }
-      if (lane == 0) s_n8 = run; else if (lane == 1) s_n4 = run; else s_nc = run;
+      if (lane == 0) s_n8 = run; else if (lane == 1) s_n4 = run; else { s_nc = run; s_ncw = off[CFIRST - 1]; }
     }
   }
   __syncthreads();
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
     }
   }
   __syncthreads();
-  const int n8 = s_n8, n4 = s_n4, nc = s_nc;
+  const int n8 = s_n8, n4 = s_n4, nc = s_nc, ncw = s_ncw;
   const bool bad_tile = s_bad != 0;
 
   // ---- phase D: warps take chunks of 32 consecutive items: 8-strips, then 4-strips, then cells ----
@@ -493,8 +501,13 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
     if (lane == 0) base = atomicAdd(&s_next, 32);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= n_items) break;
-    const int e = base + lane;
-    const bool is8 = e < n8, is4 = !is8 && e < n8 + n4, isc = !is8 && !is4 && e < n_items;
+    // item order: the ncw single cells of wide radius (scalar loop: long, and a warp does one cell per lane), then the
+    // strips, then the remaining cells -- so that nothing long is left for the end of the tile, when one warp works
+    // and the CTA still holds its half of the SM
+    const int ei = base + lane;
+    const bool iscw = ei < ncw;
+    const int e = ei - ncw;                    // index into [8-strips | 4-strips | remaining cells]
+    const bool is8 = !iscw && e < n8, is4 = !iscw && !is8 && e < n8 + n4, isc = iscw || (!is8 && !is4 && ei < n_items);
     if (USE8 && __any_sync(0xffffffffu, is8 && !bad_tile)) {
       const bool valid = is8 && !bad_tile;
       const int sid = valid ? (int)s_i8[e] : 0;
@@ -565,7 +578,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
       }
     }
     if (isc) {
-      const int lid = s_ic[e - n8 - n4];
+      const int lid = s_ic[iscw ? ei : e - n8 - n4 + ncw];
       const uint32_t b = s_nn[lid];
       const int ly = lid / TX, lx = lid - ly * TX;
       const int gx = x0 + lx, gy = y0 + ly;

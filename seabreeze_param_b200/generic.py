@@ -162,6 +162,10 @@ class Plan:
         """Most CTAs a heavy tile of the k_win8 window kernel is given to (before set_static).  See sbd_plan_set_tile_split."""
         _capi.check(self.lib.sbd_plan_set_tile_split(self._h, int(max_parts)), "plan_set_tile_split")
 
+    def set_tile_rows(self, rows):
+        """Rows per tile of the k_win8 window kernel: 0 auto (default), 16 or 32.  See sbd_plan_set_tile_rows."""
+        _capi.check(self.lib.sbd_plan_set_tile_rows(self._h, int(rows)), "plan_set_tile_rows")
+
     def window_info(self):
         """(nn, n_land, n_sea): int32 (ny, nx) arrays -- the radius at which the growing-window loop
         (G:188-214) stops for every cell and its land / sea counters; 0 outside the coastal zone."""

@@ -106,9 +106,10 @@ def test_c3_full_size_properties(oracle):
     th, dp, du, dv = haloed(t(theta)), t(p), t(u), t(v)
     res = {}
     stats = None
-    for wk in (1, 2, 3, 3):
+    for run, wk in enumerate((1, 2, 3, 3)):
         plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, nz, h)
         plan.set_window_kernel(wk)
+        plan.set_tile_rows(16 if run == 3 else 32)      # the repeat of k_win8 uses the half-height tiles: same bits
         plan.set_static(mk, zh, sh)
         info = plan.info()
         assert info["nn_max"] >= 50, info

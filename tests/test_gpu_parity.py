@@ -482,7 +482,7 @@ def test_generic_device_pointers_torch(oracle):
     plan.close()
 
 
-@pytest.mark.parametrize("wk", [0, 1, 2, 3, 38])
+@pytest.mark.parametrize("wk", [0, 1, 2, 3, 38, 316])
 @pytest.mark.parametrize("nx,ny,h,filt,expect", [(160, 96, 24, 14.0, "big tile"), (320, 240, 54, 40.0, "big tile"),
                                                    (300, 200, 72, 60.0, "global path")])
 def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
@@ -496,6 +496,9 @@ def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
     if wk == 38:     # k_win8 with 8-cell strips
         plan.set_window_kernel(3)
         plan.set_strip_cells(8)
+    elif wk == 316:  # k_win8 with 64 x 16 tiles (what a rank's block of a decomposed grid selects by itself)
+        plan.set_window_kernel(3)
+        plan.set_tile_rows(16)
     else:
         plan.set_window_kernel(wk)
     plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
@@ -527,6 +530,8 @@ def test_wide_windows_signed_class_fallback(oracle, what):
     ny, nx, h = cfg.ny, cfg.nx, cfg.h
     plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, h)
     plan.set_window_kernel(3)
+    if what == "nan":
+        plan.set_tile_rows(16)
     plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
     assert plan.info()["nn_max"] >= 12, plan.info()
     so = [np.zeros((ny, nx), np.float32) for _ in range(4)]

@@ -15,7 +15,17 @@
  * The algorithms follow the published algorithms glibc 2.39 uses for the same functions
  * (expf/sinf/cosf: double-precision polynomial kernels from ARM optimized-routines;
  * atanf/atan2f: the fdlibm binary32 kernels), so the pinned values equal this container's libm in
- * the overwhelming majority of inputs; tests/test_math_pinned.py measures the residual rate.
+ * the overwhelming majority of inputs; tests/test_math_pinned.py measures the residual rate
+ * per function and tests/test_libm_census.py on the outputs of the whole path (0 differing bits on c2 / c4).
+ *
+ * Attribution.  No code was copied; the functions below are restatements of published algorithms and use
+ * their published constants (table entries, polynomial coefficients, argument-reduction constants):
+ *   - expf, sinf, cosf: Arm Optimized Routines (math/expf.c, math/sincosf.h), Copyright (c) 2017-2019 Arm
+ *     Limited, distributed under MIT OR Apache-2.0 WITH LLVM-exception; the same routines were
+ *     contributed to glibc (sysdeps/ieee754/flt-32/e_expf.c, s_sincosf.h) under the LGPL-2.1-or-later.
+ *   - atanf, atan2f: FreeBSD msun / fdlibm (s_atanf.c, e_atan2f.c), Copyright (C) 1993 by Sun Microsystems,
+ *     Inc.  "Developed at SunPro, a Sun Microsystems, Inc. business.  Permission to use, copy, modify, and
+ *     distribute this software is freely granted, provided that this notice is preserved."
  *
  * Host+device header: no CUDA runtime dependency.
  */

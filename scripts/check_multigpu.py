@@ -82,7 +82,7 @@ for step in STEPS:
             print("step", step, nm, "identical" if same.all() else "DIFFERENT (%d cells)" % (~same).sum())
             ok &= bool(same.all())
 # third plan: peer-memory halo reads with the post / wait words handled inside the window kernel (no
-# barrier launch) and pipelined steps; all 16 steps are enqueued back to back without a host sync
+# barrier launch); all 16 steps are enqueued back to back without a host sync
 peer_f = halo.PeerHalo(len(STEPS), nyl, nx, h, rank, world, dev)
 for i, (th_i, _, _, _) in enumerate(inputs):
     pl = peer_f.plane(i)
@@ -110,14 +110,14 @@ def same_bits(x, y):
     return bool(((a_.view(np.uint32) == b_.view(np.uint32)) | (np.isnan(a_) & np.isnan(b_))).all())
 for i, step in enumerate(STEPS):
     if not same_bits(sb_hist[i], sb_f[i]):
-        print("rank", rank, "step", step, "sb_con FLAG-SYNC/PIPELINED path DIFFERENT"); ok = False
+        print("rank", rank, "step", step, "sb_con FLAG-SYNC path DIFFERENT"); ok = False
 for s_a, s_b, nm in zip(st[:3], st_f, ("ws", "wd", "thc")):
     if not same_bits(s_a, s_b):
-        print("rank", rank, nm, "final state FLAG-SYNC/PIPELINED path DIFFERENT"); ok = False
+        print("rank", rank, nm, "final state FLAG-SYNC path DIFFERENT"); ok = False
 dist.barrier()
 okt = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(okt, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("MULTIGPU_CHECK", "PASS" if int(okt.item()) else "FAIL", "world", world, "(NCCL exchange, peer-memory halo reads with barrier, and with in-kernel flags + pipelined steps, vs 1 rank)")
+    print("MULTIGPU_CHECK", "PASS" if int(okt.item()) else "FAIL", "world", world, "(NCCL exchange, peer-memory halo reads with barrier, and with in-kernel flags, vs 1 rank)")
 dist.barrier()
 dist.destroy_process_group()

@@ -61,6 +61,11 @@ def load():
                 raise SbdError(
                     "libsbd_b200.so is missing and cannot be built (%s). The sea-breeze trigger has "
                     "no CPU fallback: build it with `python -m seabreeze_param_b200.build`." % e)
+            # a prebuilt library older than its sources: usable (a box without nvcc), but say so -- results of a stale
+            # build are not the results of the code next to it
+            import warnings
+            warnings.warn("libsbd_b200.so is older than its sources and could not be rebuilt (%s); loading the stale "
+                          "library" % str(e).splitlines()[0], RuntimeWarning)
     lib = C.CDLL(path)
     vp, fp, ip, i, f = C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_float
     lib.sbd_default_params.argtypes = [C.POINTER(SbdParams), i]

@@ -12,17 +12,8 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def _have_gpu():
-    try:
-        from seabreeze_param_b200 import _capi
-        return _capi.load().sbd_device_count() > 0
-    except Exception:
-        return False
-
-
-def pytest_collection_modifyitems(config, items):
-    # `-m gpu` on a box without a GPU must fail loudly, not skip: there is no CPU fallback to test.
-    pass
+# `-m gpu` on a box without a GPU fails loudly (SBD_ECUDA from every entry point): there is no CPU fallback to test,
+# so nothing is skipped here.
 
 
 @pytest.fixture(scope="session")

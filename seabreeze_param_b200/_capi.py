@@ -22,7 +22,7 @@ SYMBOLS = [
     "sbd_plan_create", "sbd_plan_destroy", "sbd_plan_set_stream", "sbd_plan_use_own_stream", "sbd_plan_get_stream",
     "sbd_plan_sync", "sbd_plan_set_static", "sbd_plan_info", "sbd_plan_n_quads", "sbd_plan_host_split", "sbd_plan_step", "sbd_plan_step_scan", "sbd_plan_step_finish", "sbd_plan_step_py",
     "sbd_launch_count", "sbd_stats_chain_f32", "sbd_plan_set_timing", "sbd_plan_last_timing", "sbd_plan_set_halo_mode", "sbd_plan_set_peer_theta",
-    "sbd_plan_set_peer_sync", "sbd_plan_set_strip_cells", "sbd_plan_set_tile_split", "sbd_plan_set_tile_rows", "sbd_set_stats_mode", "sbd_plan_set_window_kernel", "sbd_set_window_kernel_default", "sbd_plan_set_row_window", "sbd_get_edges_ex_f32", "sbd_plan_window_info",
+    "sbd_plan_set_peer_sync", "sbd_plan_set_strip_cells", "sbd_plan_set_tile_split", "sbd_plan_set_tile_rows", "sbd_plan_set_xplane", "sbd_set_stats_mode", "sbd_plan_set_window_kernel", "sbd_set_window_kernel_default", "sbd_plan_set_row_window", "sbd_get_edges_ex_f32", "sbd_plan_window_info",
     "sbd_get_edges_f64", "sbd_get_dist_f64", "sbd_sigmoid_f64", "sbd_seabreeze_diag_f64", "sbd_swap_bounds_f64",
     "sbd_plan_cache_clear", "sbd_plan_cache_stats", "sbd_host_register", "sbd_host_unregister",
     "sbd_um_seabreeze_diag_f32", "sbd_um_get_edges_f32", "sbd_um_get_dist_f32", "sbd_um_swap_bounds_f32",
@@ -110,6 +110,7 @@ def load():
     lib.sbd_plan_set_strip_cells.argtypes = [vp, i]
     lib.sbd_plan_set_tile_split.argtypes = [vp, i]
     lib.sbd_plan_set_tile_rows.argtypes = [vp, i]
+    lib.sbd_plan_set_xplane.argtypes = [vp, i]
     lib.sbd_set_stats_mode.argtypes = [i]
     lib.sbd_plan_set_window_kernel.argtypes = [vp, i]
     lib.sbd_set_window_kernel_default.argtypes = [i]

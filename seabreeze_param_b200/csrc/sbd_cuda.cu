@@ -895,6 +895,11 @@ struct TrigArgs {
   const int* tile_order;
   int ntx;
   int prefilled;  // python variant: k_py_fill has already written the output planes of cells outside the coastal zone
+  // strip kernels: x = +t0 (land) / -t0 (sea) of every cell a tile may stage, index maps, virtual halos and
+  // neighbour-rank rows resolved, written by k_xplane just before the window kernel (NaN: t0 negative or NaN).
+  // Element (gx, gy) of the grid is at xplane[(gy + xp_R) * xp_ld + gx + xp_R].  NULL: tiles stage from theta / gzsm / code.
+  const float* xplane;
+  int xp_R, xp_ld;
 };
 
 // ---- peer flags over NVLink (system scope) ----
@@ -929,6 +934,54 @@ __device__ __forceinline__ void wait_peer_flag(uint32_t* sync_local, int which, 
     __nanosleep(64);
     if (globaltimer_ns() - t0 > 4000000000ull) { sync_local[2 + which] = seq; break; }
   }
+}
+
+// Staging source of the strip window kernels (k_win4, k_win8): one streaming pass per step that resolves, once per
+// cell instead of once per tile that stages the cell (a halo of 54 around a 64 x 32 tile: 12 x), everything the
+// tiles' staging loops used to do per element -- t0 = theta - gzsm (G:167), the land bit, the variant's index map
+// (virtual halos G / clamp + wrap quirk P:201-202), rows of the neighbour ranks read over NVLink -- and leaves
+// x = +t0 (land) / -t0 (sea); NaN marks a cell whose t0 is negative or NaN (its tiles take the per-cell global path).
+// The multi-GPU handshake of the step lives here too: block (0,0) posts, blocks of neighbour rows wait.
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_xplane(const TrigArgs a, float* __restrict__ xp, int Rx, int ld)
+{
+  const int ly = blockIdx.y, gy = ly - Rx;
+  if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      __threadfence_system();
+      if (a.sync_up) st_release_sys(a.sync_up + 1, a.sync_seq);
+      if (a.sync_dn) st_release_sys(a.sync_dn + 0, a.sync_seq);
+    }
+    const bool need_up = a.theta_up && gy < 0, need_dn = a.theta_dn && gy >= a.g.ny;
+    if (need_up || need_dn) {
+      if (threadIdx.x == 0) wait_peer_flag(a.sync_local, need_up ? 0 : 1, a.sync_seq);
+      __syncthreads();
+    }
+  }
+  const int lx = blockIdx.x * 256 + threadIdx.x;
+  if (lx >= ld) return;
+  const int gxr = lx - Rx;
+  float th, gz; uint32_t cd;
+  if (VARIANT == SBD_VARIANT_GENERIC) {
+    int gyl = gy;
+    if ((a.g.vh & 2) && gyl < 0) gyl = 0;
+    if ((a.g.vh & 4) && gyl >= a.g.ny) gyl = a.g.ny - 1;
+    const size_t rowoff = (size_t)min(max(gyl + a.g.h, 0), a.g.ldy - 1) * a.g.ldx;
+    const float* trow = a.theta + rowoff;
+    if (gy < 0 && a.theta_up) trow = a.theta_up + (size_t)(a.ny_up + gy + a.g.h) * a.g.ldx;
+    else if (gy >= a.g.ny && a.theta_dn) trow = a.theta_dn + (size_t)(gy - a.g.ny + a.g.h) * a.g.ldx;
+    int gx = gxr;
+    if (a.g.vh & 1) gx = (gx < 0) ? gx + a.g.nx : ((gx >= a.g.nx) ? gx - a.g.nx : gx);
+    const int x = min(max(gx + a.g.h, 0), a.g.ldx - 1);
+    th = trow[x]; gz = a.gzsm[rowoff + x]; cd = a.code[rowoff + x];
+  } else {
+    const int sidx = nbr_index<VARIANT>(a.g, gxr, gy);
+    th = a.theta[sidx]; gz = a.gzsm[sidx]; cd = a.code[sidx];
+  }
+  const float t0 = th - gz;                                    // G:167
+  float x = (cd >> 15) ? t0 : -t0;
+  if (!(t0 >= 0.0f)) x = __int_as_float(0x7fc00000);           // negative or NaN: signed-class form unusable
+  xp[(size_t)ly * ld + lx] = x;
 }
 
 // theta at interior-relative (gx, gy): the local plane, or -- for rows that belong to a neighbouring
@@ -1587,7 +1640,7 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
   uint32_t* s_strip = reinterpret_cast<uint32_t*>(s_nn + TX * TY);     // nn_w << 16 | strip id
   uint32_t* s_cell = s_strip + NT;                                      // byte << 16 | local cell id
   __shared__ int s_cnt[NB], s_off[NB], s_ccnt[NCB], s_coff[NCB];
-  __shared__ int s_lev, s_nstrip, s_ncell;
+  __shared__ int s_lev, s_nstrip, s_ncell, s_bad4;
 
   const int tile = a.tile_order ? (a.tile_order[blockIdx.x] & 0xfffff) : (int)blockIdx.x;   // heaviest tiles first
   const int x0 = (tile % a.ntx) * TX, y0 = (tile / a.ntx) * TY;
@@ -1596,7 +1649,7 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
 
   if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
 
-  if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {  // multi-GPU post / wait, as in k_trigger
+  if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local && !a.xplane) {  // multi-GPU post / wait, as in k_trigger (with an x-plane: done by k_xplane)
     if (blockIdx.x == 0 && tid == 0) {
       __threadfence_system();
       if (a.sync_up) st_release_sys(a.sync_up + 1, a.sync_seq);
@@ -1615,6 +1668,8 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
 
   if (tid < NB) s_cnt[tid] = 0;
   if (tid < NCB) s_ccnt[tid] = 0;
+  if (tid == 0) s_bad4 = 0;
+  if (a.xplane) __syncthreads();   // s_bad4 is set during staging
   if (VARIANT == SBD_VARIANT_PYTHON && tid == NT - 1) {  // one level for the whole grid (P:228)
     int lev = 0;
     float best = fabsf(a.p[0] - a.prm.target_plev);
@@ -1626,6 +1681,20 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
   }
 
   // ---- phase 1: stage (t_land, t_sea) of the tile + halo, one warp per row ----
+  if (a.xplane) {   // from the step's x-plane: one coalesced load per cell; a NaN marks a t0 < 0 (tile -> global path)
+    int bad = 0;
+    for (int ly = warp; ly < Hh; ly += NT / 32) {
+      const float* xrow = a.xplane + (size_t)(y0 - R + ly + a.xp_R) * a.xp_ld + (x0 - R + a.xp_R);
+      unsigned long long* srow = s_t + (size_t)ly * WP;
+#pragma unroll 4
+      for (int lx = lane; lx < W; lx += 32) {
+        const float xv = xrow[lx];
+        if (xv != xv) bad = 1;
+        srow[lx] = pack2(fmaxf(xv, -0.0f), fmaxf(-xv, -0.0f));   // the other class's slot: -0.0, the additive identity
+      }
+    }
+    if (bad) s_bad4 = 1;
+  } else
   for (int ly = warp; ly < Hh; ly += NT / 32) {
     const int gy = y0 - R + ly;
     const float* trow = nullptr; const float* grow = nullptr; const uint16_t* crow = nullptr;
@@ -1689,6 +1758,14 @@ __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
     s_nn[lid] = b;
   }
   __syncthreads();
+  if (a.xplane && s_bad4) {   // a staged t0 was negative or NaN: every coastal cell of the tile takes the global path
+#pragma unroll
+    for (int q = 0; q < TX * TY / NT; ++q) {
+      const uint8_t b = s_nn[q * NT + tid];
+      if (b) s_nn[q * NT + tid] = (uint8_t)((b & 0x80u) | 0x40u);
+    }
+    __syncthreads();
+  }
 
   // ---- phase 2b: one strip per thread, column-major (vertical neighbours in adjacent lanes) ----
   const int sx = tid / TY, sy = tid % TY;
@@ -2197,6 +2274,10 @@ struct sbd_plan {
   int* d_tile_split16 = nullptr;  // k_win8 with 64 x 16 tiles
   int n_tile_split16 = 0;
   int tile_rows = 0;          // sbd_plan_set_tile_rows: 0 auto, 16, 32
+  float* d_xplane = nullptr;  // strip kernels' staging source (k_xplane), (nty*32 + 2 xp_R) x xp_ld
+  size_t xplane_elems = 0;
+  int xp_R = 0, xp_ld = 0, xp_rows = 0;
+  int use_xplane = 0;         // sbd_plan_set_xplane (measured: no gain, see include/sbd.h)
   int tile_rows_auto = 32;    // what auto resolves to for this plan's radius plane (set_static)
   int tile_split_max = 1;     // sbd_plan_set_tile_split: most CTAs one tile is given to (measured: splitting does not pay)
   int strip_cells = 4;        // sbd_plan_set_strip_cells: cells per strip of k_win8 (4 or 8)
@@ -2483,6 +2564,29 @@ int launch_trigger_cfg(sbd_plan* p, TrigArgs& a)
 // where the search radius reaches k+1 = 55 cells).
 int g_window_kernel_default = 0;  // sbd_set_window_kernel_default
 
+// the strip kernels' staging source for this step (see k_xplane); inside the window kernel's timing bracket
+template <int VARIANT>
+int launch_xplane(sbd_plan* p, TrigArgs& a)
+{
+  a.xplane = nullptr;
+  if (!p->use_xplane) return SBD_OK;
+  const int R = a.R;
+  const int ld = ((cdiv(p->nx, 64) * 64 + 2 * R) + 3) & ~3, rows = cdiv(p->ny, 32) * 32 + 2 * R;
+  const size_t need = (size_t)ld * rows;
+  if (need > p->xplane_elems) {
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaFree(p->d_xplane));
+    p->d_xplane = nullptr; p->xplane_elems = 0;
+    CK(cudaMalloc((void**)&p->d_xplane, need * sizeof(float)));
+    p->xplane_elems = need;
+  }
+  p->xp_R = R; p->xp_ld = ld; p->xp_rows = rows;
+  dim3 grid(cdiv(ld, 256), rows);
+  k_xplane<VARIANT><<<grid, 256, 0, p->stream>>>(a, p->d_xplane, R, ld); LAUNCHED();
+  a.xplane = p->d_xplane; a.xp_R = R; a.xp_ld = ld;
+  return SBD_OK;
+}
+
 // strip form of the window kernel (k_win4): tile 64 x 32, 512 threads
 template <int VARIANT>
 int launch_win4(sbd_plan* p, TrigArgs& a)
@@ -2508,10 +2612,12 @@ int launch_win4(sbd_plan* p, TrigArgs& a)
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = (GEN && a.order == 0 && !p->timing) ? 1 : 0;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+  { int rc = launch_xplane<VARIANT>(p, a); if (rc != SBD_OK) return rc; }
+  // (with an x-plane the window kernel must see the whole of k_xplane: no programmatic early start)
+  at[0].val.programmaticStreamSerializationAllowed = (GEN && a.order == 0 && !p->timing && !a.xplane) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
   CK(cudaLaunchKernelEx(&cfg, kern, (const TrigArgs)a)); LAUNCHED();
   if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
   if (GEN && a.order == 0) {
@@ -2548,10 +2654,12 @@ int launch_win8_cfg(sbd_plan* p, TrigArgs& a)
   cfg.stream = p->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = (GEN && a.order == 0 && !p->timing) ? 1 : 0;
+  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
+  { int rc = launch_xplane<VARIANT>(p, a); if (rc != SBD_OK) return rc; }
+  // (with an x-plane the window kernel must see the whole of k_xplane: no programmatic early start)
+  at[0].val.programmaticStreamSerializationAllowed = (GEN && a.order == 0 && !p->timing && !a.xplane) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (p->timing) CK(cudaEventRecord(p->ev[0], p->stream));
   CK(cudaLaunchKernelEx(&cfg, kern, (const TrigArgs)a)); LAUNCHED();
   if (p->timing) CK(cudaEventRecord(p->ev[1], p->stream));
   if (GEN && a.order == 0) {
@@ -2720,7 +2828,7 @@ void sbd_plan_destroy(sbd_plan* p)
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->e_copy) cudaEventDestroy(p->e_copy);
   if (p->e_main) cudaEventDestroy(p->e_main);
-  cudaFree(p->d_pfull); cudaFree(p->d_join); cudaFree(p->d_tile_order); cudaFree(p->d_tile_split); cudaFree(p->d_tile_split16);
+  cudaFree(p->d_pfull); cudaFree(p->d_join); cudaFree(p->d_tile_order); cudaFree(p->d_tile_split); cudaFree(p->d_tile_split16); cudaFree(p->d_xplane);
   for (int i = 0; i < 3; ++i) cudaFree(p->d_st_in[i]);
   cudaFree(p->d_sum);
   for (auto& s : p->stage) cudaFree(s.first);
@@ -2795,6 +2903,12 @@ int sbd_plan_set_tile_split(sbd_plan* p, int max_parts)
   if (!p) return fail(SBD_EINVAL, "plan is NULL");
   if (max_parts < 1 || max_parts > 16) return fail(SBD_EINVAL, "tile split: 1..16 CTAs per tile");
   p->tile_split_max = max_parts;
+  return SBD_OK;
+}
+int sbd_plan_set_xplane(sbd_plan* p, int on)
+{
+  if (!p) return fail(SBD_EINVAL, "plan is NULL");
+  p->use_xplane = on ? 1 : 0;
   return SBD_OK;
 }
 int sbd_plan_set_tile_rows(sbd_plan* p, int rows)

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
 
   if (SPLIT && a.order == 1) asm volatile("griddepcontrol.launch_dependents;");
 
-  if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local) {  // multi-GPU post / wait, as in k_trigger
+  if (VARIANT == SBD_VARIANT_GENERIC && a.sync_local && !a.xplane) {  // multi-GPU post / wait, as in k_trigger (with an x-plane: done by k_xplane)
     if (blockIdx.x == 0 && tid == 0) {
       __threadfence_system();
       if (a.sync_up) st_release_sys(a.sync_up + 1, a.sync_seq);
@@ -365,7 +365,20 @@ __global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
   const int WP = ((W + 3) & ~3) + 4;        // multiple of 4 floats (16-byte rows), + 4: rows shift by one bank group
 
   // ---- phase B: stage x = +-t0 of the tile + halo R, one warp per row ----
-  if (R > 0) {
+  if (R > 0 && a.xplane) {   // from the step's x-plane (k_xplane): one coalesced load per cell
+    int bad = 0;
+    for (int ly = warp; ly < Hh; ly += NW) {
+      const float* xrow = a.xplane + (size_t)(y0 - R + ly + a.xp_R) * a.xp_ld + (x0 - R + a.xp_R);
+      float* srow = s_t + (size_t)ly * WP;
+#pragma unroll 6
+      for (int lx = lane; lx < W; lx += 32) {
+        const float xv = xrow[lx];
+        if (xv != xv) bad = 1;                                     // t0 negative or NaN somewhere under this tile
+        srow[lx] = xv;
+      }
+    }
+    if (bad) s_bad = 1;
+  } else if (R > 0) {
     int bad = 0;
     for (int ly = warp; ly < Hh; ly += NW) {
       const int gy = y0 - R + ly;

@@ -162,6 +162,10 @@ class Plan:
         """Most CTAs a heavy tile of the k_win8 window kernel is given to (before set_static).  See sbd_plan_set_tile_split."""
         _capi.check(self.lib.sbd_plan_set_tile_split(self._h, int(max_parts)), "plan_set_tile_split")
 
+    def set_xplane(self, on):
+        """Strip window kernels stage from the per-step x-plane (default) or from theta / gzsm / code.  See sbd_plan_set_xplane."""
+        _capi.check(self.lib.sbd_plan_set_xplane(self._h, 1 if on else 0), "plan_set_xplane")
+
     def set_tile_rows(self, rows):
         """Rows per tile of the k_win8 window kernel: 0 auto (default), 16 or 32.  See sbd_plan_set_tile_rows."""
         _capi.check(self.lib.sbd_plan_set_tile_rows(self._h, int(rows)), "plan_set_tile_rows")

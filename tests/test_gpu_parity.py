@@ -482,7 +482,7 @@ def test_generic_device_pointers_torch(oracle):
     plan.close()
 
 
-@pytest.mark.parametrize("wk", [0, 1, 2, 3, 38, 316])
+@pytest.mark.parametrize("wk", [0, 1, 2, 3, 38, 316, 201, 301])
 @pytest.mark.parametrize("nx,ny,h,filt,expect", [(160, 96, 24, 14.0, "big tile"), (320, 240, 54, 40.0, "big tile"),
                                                    (300, 200, 72, 60.0, "global path")])
 def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
@@ -496,9 +496,12 @@ def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
     if wk == 38:     # k_win8 with 8-cell strips
         plan.set_window_kernel(3)
         plan.set_strip_cells(8)
-    elif wk == 316:  # k_win8 with 64 x 16 tiles (what a rank's block of a decomposed grid selects by itself)
+    elif wk == 316:  # k_win8 with 64 x 16 tiles
         plan.set_window_kernel(3)
         plan.set_tile_rows(16)
+    elif wk in (201, 301):   # k_win4 / k_win8 staging from the per-step x-plane (k_xplane) instead of theta, gzsm, code
+        plan.set_window_kernel(wk // 100)
+        plan.set_xplane(True)
     else:
         plan.set_window_kernel(wk)
     plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])
@@ -520,8 +523,9 @@ def test_wide_windows_km_scale(oracle, nx, ny, h, filt, expect, wk):
     plan.close()
 
 
+@pytest.mark.parametrize("wk", [3, 2, 301, 201])
 @pytest.mark.parametrize("what", ["negative", "nan", "zero"])
-def test_wide_windows_signed_class_fallback(oracle, what):
+def test_wide_windows_signed_class_fallback(oracle, what, wk):
     """k_win8 keeps x = +-t0 in shared memory, which needs t0 >= +0; a tile that stages a negative or
     NaN t0 must fall back to the per-cell global path and still give the oracle's bits (NaNs included).
     t0 == 0 (both signs) stays on the fast path."""
@@ -529,7 +533,8 @@ def test_wide_windows_signed_class_fallback(oracle, what):
     case = generic_case(cfg, oracle)
     ny, nx, h = cfg.ny, cfg.nx, cfg.h
     plan = generic.Plan(SBD_VARIANT_GENERIC, nx, ny, cfg.nz, h)
-    plan.set_window_kernel(3)
+    plan.set_window_kernel(wk // 100 if wk > 100 else wk)    # k_win8, k_win4; 301 / 201: staged from the x-plane, whose
+    plan.set_xplane(wk > 100)                                 # NaN marker sends the tile to the global path
     if what == "nan":
         plan.set_tile_rows(16)
     plan.set_static(case["mask_h"], case["z_h"], case["sigma_h"])

@@ -283,9 +283,9 @@ int sbd_plan_set_peer_theta(sbd_plan* plan, const float* theta_up, int ny_up, co
  * (Re-)arming clears this rank's four words and restarts the sequence: do it on every rank between two barriers.
  * NULL sync_local switches the handshake off. */
 int sbd_plan_set_peer_sync(sbd_plan* plan, uint32_t* sync_local, uint32_t* sync_up, uint32_t* sync_dn);
-/* Form of the window-sum kernel: 0 = automatic (tile kernel k_trigger for search radii <= 8, round 1's 4-cell strip
+/* Form of the window-sum kernel: 0 = automatic (tile kernel k_trigger for search radii <= 8, the pair-layout strip
  * kernel k_win4 for 9..31, the signed-class strip kernel k_win8 from 32), 1 = tile kernel (one cell per thread, cells
- * bucketed by radius), 2 = k_win4, 3 = k_win8.  Every form evaluates each cell's sums in the reference's raster
+ * bucketed by radius), 2 = k_win4, 3 = k_win8 (four CTAs per SM up to radius 31, two beyond).  Every form evaluates each cell's sums in the reference's raster
  * order: identical bits (tests force each form on every grid class). */
 int sbd_plan_set_window_kernel(sbd_plan* plan, int mode);
 /* Cells per strip of k_win8: 4 (default) or 8 (faster only where a tile's radii are nearly uniform). */

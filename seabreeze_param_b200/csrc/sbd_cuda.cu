@@ -2632,7 +2632,7 @@ int launch_win4(sbd_plan* p, TrigArgs& a)
 }
 
 // strip form of the window kernel, round 2 (k_win8, sbd_win8.cuh): tile 64 x 32, one float per staged cell
-template <int VARIANT, int NT, bool USE8, int TY>
+template <int VARIANT, int NT, bool USE8, int TY, int MINB = 2>
 int launch_win8_cfg(sbd_plan* p, TrigArgs& a)
 {
   constexpr bool GEN = (VARIANT == SBD_VARIANT_GENERIC);
@@ -2640,7 +2640,7 @@ int launch_win8_cfg(sbd_plan* p, TrigArgs& a)
   const int R = a.R;
   const int WPmax = ((TX + 2 * R + 3) & ~3) + 4;
   const size_t smem = (size_t)WPmax * (TY + 2 * R) * 4 + TX * TY + (size_t)(TX * TY / 8 + TX * TY / 4 + TX * TY) * 2;
-  auto kern = k_win8<VARIANT, GEN, NT, USE8, TY>;
+  auto kern = k_win8<VARIANT, GEN, NT, USE8, TY, MINB>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   a.ntx = cdiv(p->nx, TX);
   a.tile_order = TY == 16 ? p->d_tile_split16 : p->d_tile_split;
@@ -2684,17 +2684,23 @@ int launch_win8(sbd_plan* p, TrigArgs& a)
   if (p->strip_cells == 8) return launch_win8_cfg<VARIANT, 256, true, 32>(p, a);
   // 64 x 16 tiles only on request (sbd_plan_set_tile_rows): measured slower, see set_static
   if ((p->tile_rows ? p->tile_rows : p->tile_rows_auto) == 16) return launch_win8_cfg<VARIANT, 256, false, 16>(p, a);
+  // radii up to 31: the tile is at most 50 KB, so four CTAs per SM fit if the kernel keeps to 64 registers (it does,
+  // with 20 bytes of spills).  c4 (radii to 22), window kernel: 289 us at two CTAs per SM, 250 at three, 237 at four
+  if (a.R < 32) return launch_win8_cfg<VARIANT, 256, false, 32, 4>(p, a);
   return launch_win8_cfg<VARIANT, 256, false, 32>(p, a);
 }
 
 template <int VARIANT>
 int launch_trigger(sbd_plan* p, TrigArgs& a)
 {
-  // radii beyond a few cells: strip kernel (see k_win4); sbd_plan_set_window_kernel overrides
+  // radii beyond a few cells: strip kernels; sbd_plan_set_window_kernel overrides
   constexpr int win4_min = 9;
   int mode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
-  // measured (profiles/r2_probe_win.txt): km-scale radii (c3, halo 54): k_win8 4.1 ms, k_win4 5.1 ms;
-  // 0.1-degree radii (c4, up to 22): k_win4 0.37 ms, k_win8 0.39-0.45 ms
+  // measured, window kernel alone: km-scale radii (c3, halo 54): k_win8 2.95 ms, k_win4 5.2 ms
+  // (profiles/r2_probe_c3.txt).  0.1-degree radii (c4, up to 22): with the same record every step and random winds
+  // (profiles/r2_probe_c4.txt) k_win8 at four CTAs per SM 0.24 ms, k_win4 0.28 ms; with a different record every step,
+  // coherent winds and the flag plane (bench.py --workload c4) k_win8 0.44 ms, k_win4 0.425 ms -- auto stays with
+  // k_win4 below radius 32
   if ((mode == 3 || (mode == 0 && a.R >= 32)) && a.R <= 56) return launch_win8<VARIANT>(p, a);
   if ((mode == 2 || (mode == 0 && a.R >= win4_min)) && a.R <= 56) return launch_win4<VARIANT>(p, a);
   if (a.R <= 16) return launch_trigger_cfg<VARIANT, 64, 16, 256, 16>(p, a);

@@ -259,8 +259,8 @@ __device__ unsigned long long g_tile_trace[4 * 16384];
 __device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-template <int VARIANT, bool SPLIT, int NT, bool USE8, int TYV>
-__global__ void __launch_bounds__(NT, 2) k_win8(const TrigArgs a)
+template <int VARIANT, bool SPLIT, int NT, bool USE8, int TYV, int MINB = 2>
+__global__ void __launch_bounds__(NT, MINB) k_win8(const TrigArgs a)
 {
 #ifdef SBD_TRACE_TILES
   const unsigned long long tr_t0 = trace_now();

@@ -900,6 +900,7 @@ struct TrigArgs {
   // Element (gx, gy) of the grid is at xplane[(gy + xp_R) * xp_ld + gx + xp_R].  NULL: tiles stage from theta / gzsm / code.
   const float* xplane;
   int xp_R, xp_ld;
+  uint32_t rt_zero;  // always 0: a zero the compiler cannot fold (k_win8 uses it to order predicate definitions)
 };
 
 // ---- peer flags over NVLink (system scope) ----

@@ -92,7 +92,7 @@ __device__ __forceinline__ uint32_t range4(int lo, int hi, int base)
 
 template <int CW>
 __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP, int lcx, int lcy, int nw, int nlo,
-                                           const int (&nq)[CW], float (&accl)[CW], float (&accs)[CW], bool valid)
+                                           const int (&nq)[CW], float (&accl)[CW], float (&accs)[CW], bool valid, uint32_t rt_zero)
 {
   constexpr int NWIN = CW + 4;               // register window: CW + 4 consecutive elements
   constexpr int NROT = NWIN / 4;             // iterations after which the window's register names repeat
@@ -215,7 +215,11 @@ __device__ __forceinline__ void strip_walk(const float* __restrict__ s_t, int WP
     const int itC = itB + min(NROT == 3 ? 6 : 8, ((NIT_w - itB) / NROT) * NROT);
     // the row predicates of the middle loop must not be set before the left-hand loop: ptxas would hoist them to the
     // top of the row and the switched loops, left with one free predicate, would wait for it at every pair of adds
-#define SBD_PRC_DEFINE _Pragma("unroll") for (int q = 0; q < CW; ++q) { prc[q] = pr[q]; asm volatile("" : "+r"(prc[q])); }
+    // (an empty asm is not enough -- ptxas sees through it, and it folds arithmetic zeros too; `rt_zero` is a zero it
+    //  cannot know, a kernel argument, and AND-ing it with a running sum ties the predicates to the end of the
+    //  left-hand loop)
+#define SBD_PRC_DEFINE const uint32_t zdep = __float_as_uint(accl[0]) & rt_zero; \
+    _Pragma("unroll") for (int q = 0; q < CW; ++q) prc[q] = pr[q] | zdep;
     int it = 0;
     if (NROT == 3) {
       for (; it < itA; it += 3) { body_mask(it, IC<0>(), IC<0>()); body_mask(it + 1, IC<4>(), IC<0>()); body_mask(it + 2, IC<8>(), IC<0>()); }
@@ -535,7 +539,7 @@ __global__ void __launch_bounds__(NT, MINB) k_win8(const TrigArgs a)
         if (nq[q] > 0) { nw = max(nw, nq[q]); nlo = min(nlo, nq[q]); }
       }
       float accl[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, accs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      strip_walk<8>(s_t, WP, R + ssx * 8, R + ssy, nw, nlo, nq, accl, accs, valid);
+      strip_walk<8>(s_t, WP, R + ssx * 8, R + ssy, nw, nlo, nq, accl, accs, valid, a.rt_zero);
       if (valid) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(NT, MINB) k_win8(const TrigArgs a)
         if (nq[q] > 0) { nw = max(nw, nq[q]); nlo = min(nlo, nq[q]); }
       }
       float accl[4] = {0.f, 0.f, 0.f, 0.f}, accs[4] = {0.f, 0.f, 0.f, 0.f};
-      strip_walk<4>(s_t, WP, R + ssx * 8 + hlf * 4, R + ssy, nw, nlo, nq, accl, accs, valid);
+      strip_walk<4>(s_t, WP, R + ssx * 8 + hlf * 4, R + ssy, nw, nlo, nq, accl, accs, valid, a.rt_zero);
       if (valid) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

@@ -10,7 +10,7 @@
 // reference arithmetic has separate multiplies and adds; include/sbd_math.h relies on it too).
 #include <cuda_runtime.h>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -524,7 +524,6 @@ __global__ void __launch_bounds__(ST_NT) k_stats_exact(const float* __restrict__
   __shared__ unsigned long long s_nlast;
   __shared__ int s_first_bad;
   __shared__ float s_state;
-  __shared__ float s_xbad;
   __shared__ float s_red[64];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n_total = (long long)nx * ny;
@@ -685,7 +684,6 @@ __global__ void __launch_bounds__(ST_NT) k_stats_exact(const float* __restrict__
           const uint32_t bits = (nb >= (1ull << 23)) ? (((uint32_t)es << 23) | (uint32_t)(nb & 0x7fffffull))
                                                      : (uint32_t)nb;
           s_state = __uint_as_float(bits) + xb;   // the reference's fp32 add
-          s_xbad = xb;
         }
         __syncthreads();
         pos = fb + 1;
@@ -1626,7 +1624,7 @@ __device__ __forceinline__ void finish_cell(const TrigArgs& a, int gx, int gy, b
 template <int VARIANT, bool SPLIT>
 __global__ void __launch_bounds__(512, 2) k_win4(const TrigArgs a)
 {
-  constexpr int TX = 64, TY = 32, NT = 512, CW = 4, NSX = TX / CW;
+  constexpr int TX = 64, TY = 32, NT = 512, CW = 4;
   constexpr int NB = 64;      // strip buckets, index = largest radius in the strip (<= 56)
   constexpr int SMALL = 6;    // strips below this radius hand their cells to the one-cell path
   constexpr int NCB = 8;      // cell buckets: 0 = wider than the tile halo (global path), 1..5 = fixed
@@ -3094,7 +3092,7 @@ static int plan_build_code(sbd_plan* p, const float* d_mask)
   if (p->variant == SBD_VARIANT_GENERIC) {
     // compacted list of coastal-zone cells, raster order (static)
     const int n2 = p->nx * p->ny;
-    cub::CountingInputIterator<int> it(0);
+    thrust::counting_iterator<int> it(0);
     ActiveFlag fl{p->d_code, p->nx, p->h, p->g.ldx};
     size_t need = 0;
     CK(cub::DeviceSelect::If(nullptr, need, it, p->d_idx, p->d_cnt + 2, n2, fl, st));

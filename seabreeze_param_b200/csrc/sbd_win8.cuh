@@ -6,26 +6,27 @@
 // T_l, T_s = sequential fp32 sums of t0 over the land / sea cells of the (2nn+1)^2 window in raster order.
 // The order is kept per cell, so the bits are the reference's; what changes is how many cells share a load.
 //
-// Measured on B200 (scripts/mb_pipes.cu, profiles/r2_mb_pipes.txt): add.rn.f32x2 (FADD2) issues at ~63
-// pair-adds/clk/SM = half the FADD instruction rate, the same flops; one LDS.64 feeding 4 FADD2 reaches 48, feeding
-// 8 FADD2 53 pair-adds/clk/SM even without bank conflicts.  Round 1's k_win4 (4 cells per thread, 8-byte
-// (t_land,t_sea) pairs in shared memory, one CTA of 512 threads per SM at halo 54) sat at ~12: 58 % of its
-// shared-memory wavefronts were bank conflicts and it had 4 warps per scheduler.  Changes:
+// The work is fixed by parity -- two dependent fp32 add chains of (2nn+1)^2 elements per cell -- so the bound is the
+// FP32 pipe (148 SMs x 128 lanes; scripts/mb_pipes.cu, profiles/r2_mb_pipes.txt) and the design goal is issue slots:
+// adds per instruction issued.  Measured on B200: add.rn.f32x2 (FADD2) issues at half the FADD instruction rate --
+// the same flops -- and does NOT leave issue slots to the instructions next to it (scripts/mb_mix.cu), and ptxas
+// will not predicate it in place, so the sums are scalar FADDs.  Round 1's k_win4 (8-byte (t_land,t_sea) pairs in
+// shared memory, one CTA of 512 threads per SM at halo 54) had 58 % bank-conflict wavefronts.  This kernel:
 //   * the tile holds ONE float per staged cell, x = +t0 for a land cell and -t0 for a sea cell ("signed class").
-//     The pair that advances both running sums is rebuilt in registers with two FMNMX (alu pipe, not the fma pipe
-//     the adds use): (t_land, t_sea) = (max(x,-0), max(-x,-0)); -0.0 is the additive identity of round-to-nearest
+//     The pair that advances both running sums is rebuilt in registers with two FMNMX:
+//     (t_land, t_sea) = (max(x,-0), max(-x,-0)); -0.0 is the additive identity of round-to-nearest
 //     (y + -0.0 == y for every y, +0.0 included), so the slot of the other class is a bit-exact no-op.  Needs
 //     t0 >= +0 (temperatures in K); a tile that stages a negative or NaN t0 takes the per-cell global path.
-//     Half the shared memory: two CTAs per SM at halo 54, and 16-byte loads carry FOUR window elements.
-//   * a thread owns a strip of EIGHT horizontally adjacent cells (four for radii 6..11): every 16-byte
-//     shared-memory load feeds 32 FADD2.  The radius is 1-Lipschitz, so the radii of a strip differ by <= 7:
-//     the 14 leading / trailing columns of a walked row (plus the <= 3 columns of 16-byte alignment) are switched
-//     per cell by bit masks, everything in between needs no predicate; rows are switched per cell only in the
-//     outermost (largest - smallest radius) rows.
+//     Half the shared memory: two CTAs per SM at halo 54 (four up to halo 31), 16-byte loads carry FOUR elements.
+//   * a thread owns a strip of FOUR horizontally adjacent cells (eight: sbd_plan_set_strip_cells, measured slower)
+//     and walks their windows in a skewed register window (strip_walk): one LDS.128 feeds 32 adds.  The radius is
+//     1-Lipschitz, so the radii of a strip differ by <= 3: only the first / last iterations of a walked row and the
+//     rows beyond the smallest radius are switched per cell; the middle loop is 86 instructions for 64 adds.
 //   * the tile's halo is the largest radius that actually occurs in the tile, not the plan-wide maximum.
-//   * work items (8-strips, 4-strips, single cells) are bucketed by radius, longest first, and handed to
-//     warps in chunks of 32 through a shared counter.
-// Tile 64 x 32 (or 64 x 16) cells, 256 threads.
+//   * work items (strips, single cells) are bucketed by radius, longest first, and handed to warps in chunks of 32
+//     through a shared counter; single cells of wide radius go first, lone wide cells walk as strips; tiles are
+//     launched heaviest first from a static list (k_tile_cost).
+// Tile 64 x 32 (or 64 x 16) cells, 256 threads.  Measured history and the dead ends: DESIGN.md section 4.3.
 
 __device__ __forceinline__ unsigned long long mkpair(float x)
 {

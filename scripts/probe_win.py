@@ -81,23 +81,42 @@ else:
     coast = torch.empty((ny, nx), dtype=torch.float32, device=dev); cdist = torch.empty_like(coast); kk = C.c_int(0)
     _capi.check(lib.sbd_py_get_edges_f32(q(t(land)), q(t(ice)), nx, ny, q(coast)))
     _capi.check(lib.sbd_py_get_dist_f32(q(coast), q(t(land)), q(t(lon)), q(t(lat)), nx, ny, 180.0, q(cdist), C.byref(kk)))
+    like = os.environ.get("PROBE_BENCHLIKE", "")     # "w": coherent winds (bench.gen_uv), "f": flag plane, "s": state threaded
+    kw = {}
+    if "w" in like:
+        import bench
+        ctx = type("Ctx", (), {"torch": torch, "dev": dev})()
+        u = bench.gen_uv(ctx, nz, ny, nx, 0, ny, 100, 0); v = bench.gen_uv(ctx, nz, ny, nx, 0, ny, 100, 1)
+    if "f" in like:
+        kw["flags"] = torch.zeros((ny, nx), dtype=torch.uint8, device=dev)
     for wk in modes:
         plan = generic.Plan(SBD_VARIANT_PYTHON, nx, ny, nz)
         plan.set_window_kernel(wk)
         plan.set_static(cdist, t(z), t(sig))
         ws = torch.zeros((ny, nx), dtype=torch.float32, device=dev); wd = torch.zeros_like(ws)
         out = torch.zeros((4, ny, nx), dtype=torch.float32, device=dev)
+        out2 = torch.zeros((4, ny, nx), dtype=torch.float32, device=dev)
+        nstep = [0]
+        def one(stepno):
+            if "s" in like:
+                o, pv = (out, out2) if nstep[0] % 2 == 0 else (out2, out)
+                plan.step_py(stepno, cfg.timestep, p, u, v, theta, pv[2], pv[3], o, **kw)
+            else:
+                plan.step_py(stepno, cfg.timestep, p, u, v, theta, ws, wd, out, **kw)
+            nstep[0] += 1
         for s in range(3):
-            plan.step_py(s + 1, cfg.timestep, p, u, v, theta, ws, wd, out)
+            one(s + 1)
         plan.sync()
         ts = []
         for s in range(6):
             flush.fill_(float(s)); torch.cuda.synchronize()
-            t0 = time.perf_counter(); plan.step_py(s + 4, cfg.timestep, p, u, v, theta, ws, wd, out); plan.sync(); ts.append(1e6 * (time.perf_counter() - t0))
+            t0 = time.perf_counter(); one(s + 4); plan.sync(); ts.append(1e6 * (time.perf_counter() - t0))
         plan.set_timing(True)
         ks = []
         for s in range(4):
-            flush.fill_(float(s)); plan.step_py(s + 10, cfg.timestep, p, u, v, theta, ws, wd, out); ks.append(plan.last_timing()[0])
+            flush.fill_(float(s)); one(s + 10); ks.append(plan.last_timing()[0])
+        if "f" in like:
+            print("   trigger cells", int(((kw["flags"] & 2) > 0).sum().item()))
         print(name, "window kernel mode", wk, plan.info()["nn_max"], "step wall us:", " ".join("%.0f" % x for x in ts),
               "| kernel us:", " ".join("%.0f" % (a * 1e3) for a in ks))
         print("   checksum", float(out[0][out[0] < 1e19].double().sum()), float(out[1].double().sum()))

@@ -831,7 +831,8 @@ def bench_c4(ctx, args, steps, warmup, short=False):
     cdist = torch.empty_like(coast)
     kk = C.c_int(0)
     _capi.check(lib.sbd_py_get_edges_f32(q(dl), q(di), nx, ny, q(coast)))
-    _capi.check(lib.sbd_py_get_dist_f32(q(coast), q(dl), q(t(lon)), q(t(lat)), nx, ny, 180.0, q(cdist), C.byref(kk)))
+    dlon, dlat = t(lon), t(lat)                        # named: a temporary would be freed (and its block reused) before the call reads it
+    _capi.check(lib.sbd_py_get_dist_f32(q(coast), q(dl), q(dlon), q(dlat), nx, ny, 180.0, q(cdist), C.byref(kk)))
     st4 = np.zeros(4, np.float32)
     generic.sigmoid(ds, stats=st4)                     # global sequential statistics of std (P:291-309)
     stats = st4[:3].copy()

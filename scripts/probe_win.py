@@ -79,8 +79,9 @@ else:
     lib = _capi.load(); q = _capi.ptr
     p = t(synth.pressure_1d(nz))
     coast = torch.empty((ny, nx), dtype=torch.float32, device=dev); cdist = torch.empty_like(coast); kk = C.c_int(0)
-    _capi.check(lib.sbd_py_get_edges_f32(q(t(land)), q(t(ice)), nx, ny, q(coast)))
-    _capi.check(lib.sbd_py_get_dist_f32(q(coast), q(t(land)), q(t(lon)), q(t(lat)), nx, ny, 180.0, q(cdist), C.byref(kk)))
+    dl, di, dlon, dlat = t(land), t(ice), t(lon), t(lat)     # named: a temporary would be freed before the call reads it
+    _capi.check(lib.sbd_py_get_edges_f32(q(dl), q(di), nx, ny, q(coast)))
+    _capi.check(lib.sbd_py_get_dist_f32(q(coast), q(dl), q(dlon), q(dlat), nx, ny, 180.0, q(cdist), C.byref(kk)))
     like = os.environ.get("PROBE_BENCHLIKE", "")     # "w": coherent winds (bench.gen_uv), "f": flag plane, "s": state threaded
     kw = {}
     if "w" in like:
@@ -89,15 +90,33 @@ else:
         u = bench.gen_uv(ctx, nz, ny, nx, 0, ny, 100, 0); v = bench.gen_uv(ctx, nz, ny, nx, 0, ny, 100, 1)
     if "f" in like:
         kw["flags"] = torch.zeros((ny, nx), dtype=torch.uint8, device=dev)
+    recs = None
+    if "r" in like:                                  # a different record (theta, u, v) every step, as bench_c4 does
+        import bench
+        ctx = type("Ctx", (), {"torch": torch, "dev": dev})()
+        nrec = int(os.environ.get("PROBE_NREC", "6"))
+        recs = [(t(bench.theta_host(cfg, 100 + r, land, lat, hour=float(r))), bench.gen_uv(ctx, nz, ny, nx, 0, ny, 100 + r, 0),
+                 bench.gen_uv(ctx, nz, ny, nx, 0, ny, 100 + r, 1)) for r in range(nrec)]
     for wk in modes:
         plan = generic.Plan(SBD_VARIANT_PYTHON, nx, ny, nz)
         plan.set_window_kernel(wk)
-        plan.set_static(cdist, t(z), t(sig))
+        if "p" in like:                              # the plan as bench_c4 builds it: row window, statistics handed in, own stream
+            st4 = np.zeros(4, np.float32)
+            generic.sigmoid(t(sig), stats=st4)
+            plan.set_row_window(0, ny)
+            stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); plan.set_stream(stream.cuda_stream)
+            plan.set_static(cdist, t(z), t(sig), stats=st4[:3].copy())
+        else:
+            plan.set_static(cdist, t(z), t(sig))
+        print("   plan info", {k: plan.info()[k] for k in ("nn_max", "n_coastal")})
         ws = torch.zeros((ny, nx), dtype=torch.float32, device=dev); wd = torch.zeros_like(ws)
         out = torch.zeros((4, ny, nx), dtype=torch.float32, device=dev)
         out2 = torch.zeros((4, ny, nx), dtype=torch.float32, device=dev)
         nstep = [0]
         def one(stepno):
+            global theta, u, v
+            if recs is not None:
+                theta, u, v = recs[nstep[0] % len(recs)]
             if "s" in like:
                 o, pv = (out, out2) if nstep[0] % 2 == 0 else (out2, out)
                 plan.step_py(stepno, cfg.timestep, p, u, v, theta, pv[2], pv[3], o, **kw)

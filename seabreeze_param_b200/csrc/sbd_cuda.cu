@@ -2684,7 +2684,8 @@ int launch_win8(sbd_plan* p, TrigArgs& a)
   // 64 x 16 tiles only on request (sbd_plan_set_tile_rows): measured slower, see set_static
   if ((p->tile_rows ? p->tile_rows : p->tile_rows_auto) == 16) return launch_win8_cfg<VARIANT, 256, false, 16>(p, a);
   // radii up to 31: the tile is at most 50 KB, so four CTAs per SM fit if the kernel keeps to 64 registers (it does,
-  // with 20 bytes of spills).  c4 (radii to 22), window kernel: 289 us at two CTAs per SM, 250 at three, 237 at four
+  // with 20 bytes of spills).  A 3600 x 1800 plane with 0.88 M coastal cells of radius <= 23, window kernel: 289 us at
+  // two CTAs per SM, 250 at three, 237 at four
   if (a.R < 32) return launch_win8_cfg<VARIANT, 256, false, 32, 4>(p, a);
   return launch_win8_cfg<VARIANT, 256, false, 32>(p, a);
 }
@@ -2695,11 +2696,9 @@ int launch_trigger(sbd_plan* p, TrigArgs& a)
   // radii beyond a few cells: strip kernels; sbd_plan_set_window_kernel overrides
   constexpr int win4_min = 9;
   int mode = p->window_kernel ? p->window_kernel : g_window_kernel_default;
-  // measured, window kernel alone: km-scale radii (c3, halo 54): k_win8 2.95 ms, k_win4 5.2 ms
-  // (profiles/r2_probe_c3.txt).  0.1-degree radii (c4, up to 22): with the same record every step and random winds
-  // (profiles/r2_probe_c4.txt) k_win8 at four CTAs per SM 0.24 ms, k_win4 0.28 ms; with a different record every step,
-  // coherent winds and the flag plane (bench.py --workload c4) k_win8 0.44 ms, k_win4 0.425 ms -- auto stays with
-  // k_win4 below radius 32
+  // measured, window kernel alone: km-scale radii (c3, halo 54): k_win8 2.87 ms, k_win4 5.2 ms
+  // (profiles/r2_probe_c3.txt); 0.1-degree radii (c4, up to 22, 1.97 M coastal cells): k_win8 at four CTAs per SM
+  // 0.428 ms, k_win4 0.430 ms (profiles/r2_probe_c4.txt) -- auto stays with k_win4 below radius 32
   if ((mode == 3 || (mode == 0 && a.R >= 32)) && a.R <= 56) return launch_win8<VARIANT>(p, a);
   if ((mode == 2 || (mode == 0 && a.R >= win4_min)) && a.R <= 56) return launch_win4<VARIANT>(p, a);
   if (a.R <= 16) return launch_trigger_cfg<VARIANT, 64, 16, 256, 16>(p, a);

@@ -302,7 +302,7 @@ int sbd_plan_set_tile_rows(sbd_plan* plan, int rows);
 /* Strip window kernels (k_win4, k_win8): 1 = a streaming pre-pass per step (k_xplane) writes x = +-t0 of every cell a
  * tile may stage -- index maps, virtual halos and neighbour-rank rows resolved once per cell -- and the tiles stage
  * from it with one coalesced load per cell; 0 (default) = tiles stage from theta / gzsm / code themselves.  Same bits
- * either way (tested).  Measured, window kernel incl. the pre-pass: c3 2.94 ms against 2.95 ms, c4 296 us against
+ * either way (tested).  Measured, window kernel incl. the pre-pass: c3 2.94 ms against 2.95 ms, a c4-sized plane 296 us against
  * 277 us -- the tiles' staging is latency that the SM's other CTA covers, the pre-pass is 15-25 us of its own. */
 int sbd_plan_set_xplane(sbd_plan* plan, int on);
 /* Process-wide: 1 = evaluate the sigmoid statistics with the plain sequential chain (one warp) instead of the exact

@@ -100,6 +100,8 @@ else:
     for wk in modes:
         plan = generic.Plan(SBD_VARIANT_PYTHON, nx, ny, nz)
         plan.set_window_kernel(wk)
+        if os.environ.get("PROBE_STRIP8") and wk == 3:
+            plan.set_strip_cells(8)
         if "p" in like:                              # the plan as bench_c4 builds it: row window, statistics handed in, own stream
             st4 = np.zeros(4, np.float32)
             generic.sigmoid(t(sig), stats=st4)
